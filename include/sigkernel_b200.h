@@ -1,0 +1,149 @@
+/*
+ * sigkernel_b200.h -- C ABI of the B200-native signature-kernel PDE solver.
+ *
+ * This is the drop-in boundary for the hot path of crispitagorico/sigkernel
+ * (reference @ 40a5831; all file:line citations are relative to the reference tree):
+ * plain pointers and sizes, no torch types.  Every pointer named "device" is a CUDA
+ * device pointer to contiguous row-major memory owned by the CALLER; nothing is
+ * allocated inside the library; every launch is asynchronous on the `stream` argument
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and re-entrant.
+ *
+ * Notation: A, B batch sizes; M, N path lengths (points); D path dimension; d dyadic
+ * order; MM = (M-1) << d, NN = (N-1) << d fine cells per axis.
+ *
+ * Return value of every int function: SKB_OK (0) or a negative SKB_ERR_* code
+ * (skb_error_string() names it).  The reference has no error reporting on its GPU path
+ * beyond Python asserts (sigkernel/sigkernel.py:222,368); the thread-per-row limit
+ * max(MM,NN) < 1024 of those asserts does not exist here.
+ */
+#ifndef SIGKERNEL_B200_H
+#define SIGKERNEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums (plain ints in the ABI) ------------------------------------------------ */
+
+/* static kernel evaluated on the fly (sigkernel/static_kernels.py:11-73) */
+#define SKB_STATIC_LINEAR 0 /* k(x,y) = param * <x,y>; param = scale^2 for batch_kernel (:24), 1 for Gram_matrix (:33) */
+#define SKB_STATIC_RBF    1 /* k(x,y) = exp(-|x-y|^2 / param); param = sigma (:42-73) */
+
+/* finite-difference scheme of the Goursat PDE (sigkernel/cython_backend.pyx:27,30,91,94,114,116) */
+#define SKB_SCHEME_S2 0 /* default: (u10+u01)(1 + g/2 + g^2/12) - u00 (1 - g^2/12) */
+#define SKB_SCHEME_S1 1 /* _naive_solver=True: (u10+u01)(1 + g/2) - u00 */
+
+/* which (a,b) pairs are solved */
+#define SKB_PAIRS_GRAM  0 /* all A*B pairs, out[a*B+b]           (sigkernel_Gram_cuda, cuda_backend.py:121-160) */
+#define SKB_PAIRS_BATCH 1 /* pairs (a,a), requires A == B, out[a] (sigkernel_cuda, cuda_backend.py:6-49) */
+#define SKB_PAIRS_SYM   2 /* X is Y: solve a<=b, mirror into out[b*A+a] (cython_backend.pyx:76-97) */
+
+/* arithmetic mode of the stencil */
+#define SKB_ARITH_FMA   0 /* fused multiply-add form, 3 fp64 instructions per cell (default, fastest) */
+#define SKB_ARITH_EXACT 1 /* the reference's operation order with no FMA contraction: bit-identical
+                             to cython_backend.pyx given identical increments (4 instructions per cell) */
+
+/* element type of host-facing path / output buffers */
+#define SKB_F64 0
+#define SKB_F32 1
+
+#define SKB_OK               0
+#define SKB_ERR_BAD_SHAPE   -1 /* non-positive size, M or N < 2, BATCH/SYM with A != B ... */
+#define SKB_ERR_BAD_ENUM    -2 /* unknown static kind / scheme / pairs / arith / dtype */
+#define SKB_ERR_WORKSPACE   -3 /* workspace pointer NULL or smaller than skb_*_workspace_bytes() */
+#define SKB_ERR_UNSUPPORTED -4 /* shape outside what this build instantiates (see skb_error_string) */
+#define SKB_ERR_CUDA        -5 /* a CUDA call failed; skb_last_cuda_error() has the cudaError_t */
+#define SKB_ERR_NULL        -6 /* a required pointer is NULL */
+
+const char* skb_error_string(int code);
+int         skb_last_cuda_error(void);     /* cudaError_t of the last SKB_ERR_CUDA on this thread */
+int         skb_version(void);             /* ABI version, bumped on any signature change */
+
+/* Tuning knob (process-wide, default 0 = automatic): resident solver warps per SM. */
+void skb_set_warps_per_sm(int warps);
+
+/* Diagnostic used by bench.py for the roofline denominator: launches a register-resident chain of
+ * fp64 instructions (op 0 = DFMA, 1 = DADD, 2 = DMUL); blocks*threads*iters*16 thread-level DP
+ * instructions per launch, timed by the caller with CUDA events on `stream`.  threads <= 256. */
+int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream);
+
+/* ---- forward: fused static kernel + increments + dyadic refinement + PDE solve ----- */
+
+/* Bytes of caller-provided scratch the forward entry points need. */
+size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D);
+
+/*
+ * out[pairs] = signature kernel k(X_a, Y_b) for the pair set `pairs`.
+ * Replaces, in one launch sequence and without materialising any (A,B,MM,NN) tensor:
+ *   static_kernel.Gram_matrix / batch_kernel      static_kernels.py:17-33, 42-73
+ *   second difference + tile()                     sigkernel.py:217-218, 362-364, 607-613
+ *   sigkernel_Gram_cuda / sigkernel_cuda launch    sigkernel.py:224-234, 370-382; cuda_backend.py:6-49, 121-160
+ *   (= sigkernel_Gram_cython / sigkernel_cython    cython_backend.pyx:7-33, 64-119 on the CPU branch)
+ * and the final slice K[..., -1, -1] (sigkernel.py:253, 401).
+ *
+ * X (A,M,D), Y (B,N,D): device, element type `io_dtype`.  out: device, fp64, A*B entries
+ * (GRAM, SYM) or A entries (BATCH).  Arithmetic is fp64 regardless of io_dtype.
+ */
+int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype,
+                      int A, int B, int M, int N, int D, int dyadic_order,
+                      int static_kind, double static_param, int scheme, int pairs, int arith,
+                      double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Plugin path: the caller evaluated an arbitrary static kernel itself
+ * (any object with Gram_matrix / batch_kernel, static_kernels.py:75-206) and passes the
+ * COARSE matrix Ks: (A,B,M,N) for GRAM/SYM, (A,M,N) for BATCH, device fp64.  Second
+ * difference and dyadic refinement happen on the fly.  With SKB_ARITH_EXACT the result is
+ * bit-identical to the reference CPU branch fed the same Ks.
+ */
+int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
+                                  int scheme, int pairs, int arith,
+                                  double* out, void* stream);
+
+/*
+ * Operator-level mirror of the reference's L3->L1 call (sigkernel.py:378-380 /
+ * cython_backend.pyx:64): the caller built the fine increment tensor inc (P,MM,NN) itself;
+ * out[p] = u[MM,NN].  With SKB_ARITH_EXACT bit-identical to sigkernel_Gram_cython(...)[..,-1,-1].
+ */
+int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, int scheme, int arith,
+                                   double* out, void* stream);
+
+/* ---- backward: adjoint (reversed) PDE -> per-point gradients ---------------------- */
+
+size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
+
+/*
+ * Forward value AND the reference's `grad_points` in one call (the reference computes the
+ * backward eagerly inside forward when X.requires_grad, sigkernel.py:397-399):
+ *   out[pairs]                 as skb_sigkernel_fwd
+ *   grad_points (pairs, M, D)  d k(X_a,Y_b) / d X_a[p,:]  as defined by prep_backward /
+ *                              _SigKernel.backward (sigkernel.py:419-502, 256-343): reversed PDE,
+ *                              GG = u * u_rev, sum of GG * d inc / d x over the cells touching point p,
+ *                              with the ANALYTIC static-kernel derivative in place of the reference's
+ *                              h = 1e-9 one-sided finite difference (agrees with it to its own noise floor,
+ *                              SURVEY.md 8(a)).
+ * SYM is accepted for `pairs`; all A*A entries of grad_points are written.
+ */
+int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
+                          int A, int B, int M, int N, int D, int dyadic_order,
+                          int static_kind, double static_param, int scheme, int pairs,
+                          double* out, double* grad_points,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Plugin path of the backward: coarse sensitivities
+ *   S[pair, i, j] = 4^-d * sum over the fine cells (p,q) of coarse cell (i,j) of u[p,q] * u_rev[p+1,q+1]
+ * (pairs, M-1, N-1), from the coarse static matrix Ks.  The caller contracts S with its own
+ * d inc / d x (finite-difference Gram_matrix(X+h e_d, Y) exactly as sigkernel.py:473-487 does).
+ */
+int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
+                                          int scheme, int pairs, double* out, double* S,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGKERNEL_B200_H */

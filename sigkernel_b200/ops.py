@@ -1,0 +1,130 @@
+"""Operator-level wrappers: torch CUDA tensors in, torch CUDA tensors out, through the C ABI.
+
+These mirror the reference's L3 -> L1 operator calls (sigkernel/sigkernel.py:224-234, 370-382,
+440-467 and cython_backend.pyx:7, 64): PyTorch is used for device memory and streams only.
+Every function requires CUDA tensors; there is no CPU path (the reference's Cython branch is the
+parity oracle of this project, not a product path).
+"""
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_PAIRS = {"gram": _lib.PAIRS_GRAM, "batch": _lib.PAIRS_BATCH, "sym": _lib.PAIRS_SYM}
+_STATIC = {"linear": _lib.STATIC_LINEAR, "rbf": _lib.STATIC_RBF}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _io(X, Y):
+    if not (X.is_cuda and Y.is_cuda):
+        raise _lib.SigKernelB200Error("sigkernel_b200 runs on CUDA tensors only (no CPU fallback); move X, Y to a GPU")
+    if X.dtype != Y.dtype or X.dtype not in (torch.float64, torch.float32):
+        raise _lib.SigKernelB200Error(f"X and Y must both be float64 or float32, got {X.dtype}, {Y.dtype}")
+    if X.dim() != 3 or Y.dim() != 3 or X.shape[2] != Y.shape[2]:
+        raise _lib.SigKernelB200Error(f"expected (batch, length, dim) paths with equal dim, got {tuple(X.shape)}, {tuple(Y.shape)}")
+    return X.detach().contiguous(), Y.detach().contiguous(), (_lib.F64 if X.dtype == torch.float64 else _lib.F32)
+
+
+def _n_out(A, B, pairs):
+    return A if pairs == "batch" else A * B
+
+
+def sigkernel_forward(X, Y, static_kind, static_param, dyadic_order, pairs="gram", naive=False, exact=False):
+    """k(X_a, Y_b) for the pair set: (A,B) for 'gram'/'sym', (A,) for 'batch'.  fp64 result."""
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    with torch.cuda.device(Xc.device):
+        out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Xc.device)
+        nbytes = lib.skb_fwd_workspace_bytes(A, B, M, N, D)
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Xc.device)
+        check(lib.skb_sigkernel_fwd(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                    _STATIC[static_kind], float(static_param),
+                                    _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                    _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
+                                    out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    return out if pairs == "batch" else out.view(A, B)
+
+
+def sigkernel_forward_from_static(Ks, dyadic_order, pairs="gram", naive=False, exact=False):
+    """Plugin path: Ks is the coarse static matrix (A,B,M,N) ('gram'/'sym') or (A,M,N) ('batch')."""
+    if not Ks.is_cuda:
+        raise _lib.SigKernelB200Error("sigkernel_b200 runs on CUDA tensors only (no CPU fallback)")
+    Kc = Ks.detach().to(torch.float64).contiguous()
+    if pairs == "batch":
+        A, M, N = Kc.shape
+        B = A
+    else:
+        A, B, M, N = Kc.shape
+    with torch.cuda.device(Kc.device):
+        out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Kc.device)
+        check(lib.skb_sigkernel_fwd_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
+                                                _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                                _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
+                                                out.data_ptr(), _stream()))
+    return out if pairs == "batch" else out.view(A, B)
+
+
+def solve_increments(inc, naive=False, exact=True):
+    """inc (..., MM, NN) fine increments -> u[MM,NN] per leading index (operator-level entry point)."""
+    if not inc.is_cuda:
+        raise _lib.SigKernelB200Error("sigkernel_b200 runs on CUDA tensors only (no CPU fallback)")
+    lead = inc.shape[:-2]
+    MM, NN = inc.shape[-2:]
+    ic = inc.detach().to(torch.float64).contiguous().view(-1, MM, NN)
+    P = ic.shape[0]
+    with torch.cuda.device(ic.device):
+        out = torch.empty(P, dtype=torch.float64, device=ic.device)
+        check(lib.skb_sigkernel_solve_increments(ic.data_ptr(), P, MM, NN,
+                                                 _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
+                                                 _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
+                                                 out.data_ptr(), _stream()))
+    return out.view(lead)
+
+
+def sigkernel_forward_backward(X, Y, static_kind, static_param, dyadic_order, pairs="gram", naive=False):
+    """(k, grad_points): grad_points is (A,B,M,D) for 'gram'/'sym', (A,M,D) for 'batch' (fp64)."""
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    with torch.cuda.device(Xc.device):
+        n = _n_out(A, B, pairs)
+        out = torch.empty(n, dtype=torch.float64, device=Xc.device)
+        gp = torch.empty((n, M, D), dtype=torch.float64, device=Xc.device)
+        nbytes = lib.skb_bwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs])
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Xc.device)
+        check(lib.skb_sigkernel_fwd_bwd(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                        _STATIC[static_kind], float(static_param),
+                                        _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                        out.data_ptr(), gp.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    if pairs == "batch":
+        return out, gp
+    return out.view(A, B), gp.view(A, B, M, D)
+
+
+def sensitivity_from_static(Ks, dyadic_order, pairs="gram", naive=False):
+    """Plugin path of the backward: (k, S) with S the coarse sensitivities (pairs, M-1, N-1)."""
+    if not Ks.is_cuda:
+        raise _lib.SigKernelB200Error("sigkernel_b200 runs on CUDA tensors only (no CPU fallback)")
+    Kc = Ks.detach().to(torch.float64).contiguous()
+    if pairs == "batch":
+        A, M, N = Kc.shape
+        B = A
+    else:
+        A, B, M, N = Kc.shape
+    with torch.cuda.device(Kc.device):
+        n = _n_out(A, B, pairs)
+        out = torch.empty(n, dtype=torch.float64, device=Kc.device)
+        S = torch.empty((n, M - 1, N - 1), dtype=torch.float64, device=Kc.device)
+        nbytes = lib.skb_bwd_workspace_bytes(A, B, M, N, 1, int(dyadic_order), _PAIRS[pairs])
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Kc.device)
+        check(lib.skb_sigkernel_sensitivity_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
+                                                        _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
+                                                        _PAIRS[pairs], out.data_ptr(), S.data_ptr(),
+                                                        ws.data_ptr(), nbytes, _stream()))
+    if pairs == "batch":
+        return out, S
+    return out.view(A, B), S.view(A, B, M - 1, N - 1)
