@@ -70,10 +70,18 @@ void skb_set_warps_per_sm(int warps);
  * instructions per launch, timed by the caller with CUDA events on `stream`.  threads <= 256. */
 int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream);
 
-/* ---- forward: fused static kernel + increments + dyadic refinement + PDE solve ----- */
-
-/* Bytes of caller-provided scratch the forward entry points need. */
+/* ---- workspaces -------------------------------------------------------------------
+ * Every compute entry point takes a caller-owned device scratch buffer (256-byte aligned) that
+ * holds the job-queue counter, the prepared paths and (backward) the forward solution grids.
+ * The *_workspace_bytes functions return the size to allocate; 0 means bad arguments. */
 size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D);
+size_t skb_aux_workspace_bytes(void);   /* from_static / solve_increments */
+/* Recommended size for the backward entry points: room for the forward grids of all pairs,
+ * capped at 8 GiB.  Any size >= the room for ONE pair's grid is accepted: the pairs are then
+ * processed in chunks that fit. */
+size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
+
+/* ---- forward: fused static kernel + increments + dyadic refinement + PDE solve ----- */
 
 /*
  * out[pairs] = signature kernel k(X_a, Y_b) for the pair set `pairs`.
@@ -86,6 +94,7 @@ size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D);
  *
  * X (A,M,D), Y (B,N,D): device, element type `io_dtype`.  out: device, fp64, A*B entries
  * (GRAM, SYM) or A entries (BATCH).  Arithmetic is fp64 regardless of io_dtype.
+ * `arith` must be SKB_ARITH_FMA here (the fused static kernel is not bit-comparable anyway).
  */
 int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype,
                       int A, int B, int M, int N, int D, int dyadic_order,
@@ -101,7 +110,7 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype,
  */
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
                                   int scheme, int pairs, int arith,
-                                  double* out, void* stream);
+                                  double* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Operator-level mirror of the reference's L3->L1 call (sigkernel.py:378-380 /
@@ -109,11 +118,9 @@ int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, 
  * out[p] = u[MM,NN].  With SKB_ARITH_EXACT bit-identical to sigkernel_Gram_cython(...)[..,-1,-1].
  */
 int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, int scheme, int arith,
-                                   double* out, void* stream);
+                                   double* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- backward: adjoint (reversed) PDE -> per-point gradients ---------------------- */
-
-size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
 
 /*
  * Forward value AND the reference's `grad_points` in one call (the reference computes the
@@ -125,7 +132,7 @@ size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_ord
  *                              with the ANALYTIC static-kernel derivative in place of the reference's
  *                              h = 1e-9 one-sided finite difference (agrees with it to its own noise floor,
  *                              SURVEY.md 8(a)).
- * SYM is accepted for `pairs`; all A*A entries of grad_points are written.
+ * `pairs` is SKB_PAIRS_GRAM or SKB_PAIRS_BATCH (a symmetric Gram needs every (a,b) gradient anyway).
  */
 int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
                           int A, int B, int M, int N, int D, int dyadic_order,
@@ -138,6 +145,7 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
  *   S[pair, i, j] = 4^-d * sum over the fine cells (p,q) of coarse cell (i,j) of u[p,q] * u_rev[p+1,q+1]
  * (pairs, M-1, N-1), from the coarse static matrix Ks.  The caller contracts S with its own
  * d inc / d x (finite-difference Gram_matrix(X+h e_d, Y) exactly as sigkernel.py:473-487 does).
+ * `pairs` is SKB_PAIRS_GRAM or SKB_PAIRS_BATCH.
  */
 int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
                                           int scheme, int pairs, double* out, double* S,

@@ -1,9 +1,12 @@
 // skb_api.cu -- the extern "C" boundary declared in include/sigkernel_b200.h.
 // Argument validation, workspace carving and kernel dispatch only; no allocation, no sync.
 #include <string.h>
+#include "skb_common.cuh"
 #include "skb_host.h"
 
 namespace skb {
+
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3;
 
 static thread_local int g_last_cuda = 0;
 
@@ -14,7 +17,8 @@ int check_cuda(cudaError_t e) {
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-static inline int padded_dim(int D) { return (D + 2) & ~1; }   // 1 norm slot + D, rounded up to even
+static const size_t kCounterBytes = 256;
+static const size_t kScratchBudget = (size_t)8 << 30;
 
 static int check_common(int A, int B, int M, int N, int dyadic_order, int scheme, int pairs, int arith) {
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || dyadic_order < 0 || dyadic_order > 20) return SKB_ERR_BAD_SHAPE;
@@ -43,6 +47,29 @@ static void prep_factors(int kind, double param, double& cx, double& nsc) {
     }
 }
 
+static double scale4_of(int d) { return 1.0 / (double)(1ull << (2 * d)); }
+
+// bytes of forward grid one pair needs in the adjoint scratch, and the front pad
+static size_t grid_doubles_per_pair(int M, int N, int d) {
+    const int R = solver_rows_per_lane(M, d);
+    if (R < 0) return 0;
+    return (size_t)((long)(N - 1) << d) * (size_t)(32L * R);
+}
+static size_t front_pad_doubles(int M, int d) {
+    const int R = solver_rows_per_lane(M, d);
+    return R < 0 ? 0 : (size_t)(32L * R);
+}
+
+static KArgs base_args(int A, int B, int M, int N, int d, int scheme, int pairs) {
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A; a.B = B; a.M = M; a.N = N; a.Mv = M; a.Nv = N;
+    a.pairs = pairs;
+    a.s1 = scheme == SKB_SCHEME_S1;
+    a.scale4 = scale4_of(d);
+    return a;
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -53,9 +80,9 @@ const char* skb_error_string(int code) {
     switch (code) {
         case SKB_OK: return "ok";
         case SKB_ERR_BAD_SHAPE: return "bad shape (sizes must be positive, M,N >= 2, BATCH/SYM need A == B, SYM needs M == N)";
-        case SKB_ERR_BAD_ENUM: return "unknown enum value (static kind / scheme / pairs / arith / dtype)";
+        case SKB_ERR_BAD_ENUM: return "unknown or unsupported enum value (static kind / scheme / pairs / arith / dtype)";
         case SKB_ERR_WORKSPACE: return "workspace missing or too small (see skb_*_workspace_bytes)";
-        case SKB_ERR_UNSUPPORTED: return "shape not instantiated in this build";
+        case SKB_ERR_UNSUPPORTED: return "shape not instantiated in this build (needs ceil(M/32 rounded to a power of two) * 2^dyadic_order <= 32)";
         case SKB_ERR_CUDA: return "CUDA error (see skb_last_cuda_error)";
         case SKB_ERR_NULL: return "required pointer is NULL";
         default: return "unknown error code";
@@ -63,13 +90,30 @@ const char* skb_error_string(int code) {
 }
 
 int skb_last_cuda_error(void) { return g_last_cuda; }
-int skb_version(void) { return 1; }
+int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
 
 size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D) {
     if (A <= 0 || B <= 0 || M <= 0 || N <= 0 || D <= 0) return 0;
     const size_t Dp = (size_t)padded_dim(D);
-    return align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double));
+    return kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double));
+}
+
+size_t skb_aux_workspace_bytes(void) { return kCounterBytes; }
+
+size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0) return 0;
+    const size_t per = grid_doubles_per_pair(M, N, dyadic_order) * sizeof(double);
+    if (per == 0) return 0;
+    const size_t Dp = (size_t)padded_dim(D);
+    const size_t fixed = kCounterBytes + 2 * align256((size_t)A * M * Dp * sizeof(double)) +
+                         2 * align256((size_t)B * N * Dp * sizeof(double)) +
+                         align256(front_pad_doubles(M, dyadic_order) * sizeof(double));
+    size_t jobs = (size_t)njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
+    size_t cap = kScratchBudget / per;
+    if (cap < 1) cap = 1;
+    if (jobs > cap) jobs = cap;
+    return fixed + align256(jobs * per);
 }
 
 int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
@@ -80,87 +124,141 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
+    if (arith != SKB_ARITH_FMA) return SKB_ERR_BAD_ENUM;
     if (!X || !Y || !out) return SKB_ERR_NULL;
     if (!workspace || workspace_bytes < skb_fwd_workspace_bytes(A, B, M, N, D)) return SKB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int Dp = padded_dim(D);
-    double* Xp = (double*)workspace;
-    double* Yp = (double*)((char*)workspace + align256((size_t)A * M * Dp * sizeof(double)));
+    char* w = (char*)workspace;
+    unsigned int* counter = (unsigned int*)w;
+    double* Xp = (double*)(w + kCounterBytes);
+    double* Yp = (double*)(w + kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)));
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
-    rc = launch_prep(X, io_dtype, Xp, (long)A * M, D, Dp, cx, nsc, st);
+    rc = launch_prep(X, io_dtype, Xp, nullptr, A, M, D, Dp, cx, nsc, st);
     if (rc) return rc;
-    rc = launch_prep(Y, io_dtype, Yp, (long)B * N, D, Dp, 1.0, nsc, st);
+    rc = launch_prep(Y, io_dtype, Yp, nullptr, B, N, D, Dp, 1.0, nsc, st);
     if (rc) return rc;
 
-    FwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.Xp = Xp; a.Yp = Yp; a.Ks = nullptr; a.out = out;
-    a.njobs = njobs_of(A, B, pairs);
-    a.A = A; a.B = B; a.M = M; a.N = N; a.Mv = M; a.Nv = N; a.Dp = Dp;
-    a.kind = static_kind == SKB_STATIC_RBF ? 1 : 0;
-    a.pairs = pairs;
-    a.s1 = scheme == SKB_SCHEME_S1;
-    a.scale4 = 1.0 / (double)(1ull << (2 * dyadic_order));
-    return launch_forward(a, dyadic_order, arith == SKB_ARITH_EXACT, st);
+    KArgs a = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    a.Xp = Xp; a.Yp = Yp; a.out = out; a.counter = counter;
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    a.njobs = (int)nj;
+    a.Dp = Dp; a.D = D;
+    return launch_solver(MODE_FWD, static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, dyadic_order, false, a, st);
 }
 
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order, int scheme,
-                                  int pairs, int arith, double* out, void* stream) {
+                                  int pairs, int arith, double* out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, arith);
     if (rc) return rc;
     if (!Ks || !out) return SKB_ERR_NULL;
-    FwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.Ks = Ks; a.out = out;
-    a.njobs = njobs_of(A, B, pairs);
-    a.A = A; a.B = B; a.M = M; a.N = N; a.Mv = M; a.Nv = N; a.Dp = 0;
-    a.kind = 2;
-    a.pairs = pairs;
-    a.s1 = scheme == SKB_SCHEME_S1;
-    a.scale4 = 1.0 / (double)(1ull << (2 * dyadic_order));
-    return launch_forward(a, dyadic_order, arith == SKB_ARITH_EXACT, (cudaStream_t)stream);
+    if (!workspace || workspace_bytes < kCounterBytes) return SKB_ERR_WORKSPACE;
+    KArgs a = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    a.Ks = Ks; a.out = out; a.counter = (unsigned int*)workspace;
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    a.njobs = (int)nj;
+    return launch_solver(MODE_FWD, KIND_STATIC, dyadic_order, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
 }
 
 int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, int scheme, int arith,
-                                   double* out, void* stream) {
+                                   double* out, void* workspace, size_t workspace_bytes, void* stream) {
     if (P <= 0 || MM < 1 || NN < 1 || P > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
     if (arith != SKB_ARITH_FMA && arith != SKB_ARITH_EXACT) return SKB_ERR_BAD_ENUM;
     if (!inc || !out) return SKB_ERR_NULL;
-    FwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.Ks = inc; a.out = out;
-    a.njobs = P;
-    a.A = (int)P; a.B = (int)P; a.M = MM + 1; a.N = NN + 1; a.Mv = MM; a.Nv = NN; a.Dp = 0;
-    a.kind = 3;
-    a.pairs = SKB_PAIRS_BATCH;
-    a.s1 = scheme == SKB_SCHEME_S1;
-    a.scale4 = 1.0;
-    return launch_forward(a, 0, arith == SKB_ARITH_EXACT, (cudaStream_t)stream);
+    if (!workspace || workspace_bytes < kCounterBytes) return SKB_ERR_WORKSPACE;
+    KArgs a = base_args((int)P, (int)P, MM + 1, NN + 1, 0, scheme, SKB_PAIRS_BATCH);
+    a.Mv = MM; a.Nv = NN;
+    a.Ks = inc; a.out = out; a.counter = (unsigned int*)workspace;
+    a.njobs = (int)P;
+    return launch_solver(MODE_FWD, KIND_INC, 0, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
 }
 
-size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
-    (void)A; (void)B; (void)M; (void)N; (void)D; (void)dyadic_order; (void)pairs;
-    return 0;
+// shared driver of the two backward entry points: forward-with-store then reversed sweep, in chunks
+// of pairs whose forward grids fit the scratch part of the workspace
+static int run_adjoint(int kind, int rev_mode, KArgs fa, KArgs ra, int d, long njobs, double* scratch_base,
+                       size_t scratch_bytes, cudaStream_t st) {
+    const size_t per = grid_doubles_per_pair(fa.M, fa.N, d) * sizeof(double);
+    const size_t pad = front_pad_doubles(fa.M, d) * sizeof(double);
+    if (per == 0) return SKB_ERR_UNSUPPORTED;
+    if (scratch_bytes < align256(pad) + per) return SKB_ERR_WORKSPACE;
+    long chunk = (long)((scratch_bytes - align256(pad)) / per);
+    if (chunk > njobs) chunk = njobs;
+    double* grid = (double*)((char*)scratch_base + align256(pad));
+    for (long j0 = 0; j0 < njobs; j0 += chunk) {
+        const int nj = (int)(njobs - j0 < chunk ? njobs - j0 : chunk);
+        fa.job0 = ra.job0 = j0;
+        fa.njobs = ra.njobs = nj;
+        fa.scratch = ra.scratch = grid;
+        int rc = launch_solver(MODE_FWD_STORE, kind, d, false, fa, st);
+        if (rc) return rc;
+        rc = launch_solver(rev_mode, kind, d, false, ra, st);
+        if (rc) return rc;
+    }
+    return SKB_OK;
 }
 
 int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
                           int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
                           double* out, double* grad_points, void* workspace, size_t workspace_bytes,
                           void* stream) {
-    (void)X; (void)Y; (void)io_dtype; (void)A; (void)B; (void)M; (void)N; (void)D; (void)dyadic_order;
-    (void)static_kind; (void)static_param; (void)scheme; (void)pairs; (void)out; (void)grad_points;
-    (void)workspace; (void)workspace_bytes; (void)stream;
-    return SKB_ERR_UNSUPPORTED;
+    int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
+    if (rc) return rc;
+    if (pairs == SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;
+    if (D <= 0) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
+    if (!X || !Y || !out || !grad_points) return SKB_ERR_NULL;
+    if (!workspace) return SKB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Dp = padded_dim(D);
+    const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
+    const size_t fixed = kCounterBytes + 2 * xb + 2 * yb;
+    if (workspace_bytes < fixed) return SKB_ERR_WORKSPACE;
+    char* w = (char*)workspace;
+    unsigned int* counter = (unsigned int*)w;
+    double* Xp = (double*)(w + kCounterBytes);
+    double* Yp = (double*)(w + kCounterBytes + xb);
+    double* Xr = (double*)(w + kCounterBytes + xb + yb);
+    double* Yr = (double*)(w + kCounterBytes + 2 * xb + yb);
+    double cx, nsc;
+    prep_factors(static_kind, static_param, cx, nsc);
+    rc = launch_prep(X, io_dtype, Xp, Xr, A, M, D, Dp, cx, nsc, st);
+    if (rc) return rc;
+    rc = launch_prep(Y, io_dtype, Yp, Yr, B, N, D, Dp, 1.0, nsc, st);
+    if (rc) return rc;
+
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    fa.Xp = Xp; fa.Yp = Yp; fa.out = out; fa.counter = counter; fa.Dp = Dp; fa.D = D;
+    KArgs ra = fa;
+    ra.Xp = Xr; ra.Yp = Yr; ra.out = nullptr; ra.grad = grad_points;
+    ra.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
+    return run_adjoint(static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, MODE_REV_GRAD, fa, ra, dyadic_order,
+                       nj, (double*)(w + fixed), workspace_bytes - fixed, st);
 }
 
 int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
                                           int scheme, int pairs, double* out, double* S, void* workspace,
                                           size_t workspace_bytes, void* stream) {
-    (void)Ks; (void)A; (void)B; (void)M; (void)N; (void)dyadic_order; (void)scheme; (void)pairs; (void)out;
-    (void)S; (void)workspace; (void)workspace_bytes; (void)stream;
-    return SKB_ERR_UNSUPPORTED;
+    int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
+    if (rc) return rc;
+    if (pairs == SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;
+    if (!Ks || !out || !S) return SKB_ERR_NULL;
+    if (!workspace || workspace_bytes < kCounterBytes) return SKB_ERR_WORKSPACE;
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    fa.Ks = Ks; fa.out = out; fa.counter = (unsigned int*)workspace;
+    KArgs ra = fa;
+    ra.out = nullptr; ra.S = S;
+    return run_adjoint(KIND_STATIC, MODE_REV_S, fa, ra, dyadic_order, nj, (double*)((char*)workspace + kCounterBytes),
+                       workspace_bytes - kCounterBytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,108 @@
+// skb_dispatch.cu -- path preparation kernel and the host-side dispatcher of solver_kernel.
+#include "skb_common.cuh"
+#include "skb_host.h"
+
+namespace skb {
+
+// X (batch, len, D) of type T -> Xp (batch, len, Dp) rows (nscale*|x|^2, c*x_0 .. c*x_{D-1}, 0 ...),
+// optionally also the copy reversed along the length axis (the adjoint sweep solves the PDE of the
+// reversed paths, sigkernel.py:434-438).
+template <typename T>
+__global__ void prep_kernel(const T* __restrict__ X, double* __restrict__ Xp, double* __restrict__ Xp_rev,
+                            long batch, int len, int D, int Dp, double c, double nscale) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= batch * len) return;
+    const T* x = X + r * D;
+    const long bi = r / len;
+    const int li = (int)(r - bi * len);
+    double* o = Xp + r * Dp;
+    double* orv = Xp_rev ? Xp_rev + (bi * len + (len - 1 - li)) * Dp : nullptr;
+    double n = 0.0;
+    for (int k = 0; k < D; ++k) {
+        const double v = (double)x[k];
+        n = fma(v, v, n);
+        o[1 + k] = v * c;
+        if (orv) orv[1 + k] = v * c;
+    }
+    o[0] = n * nscale;
+    if (orv) orv[0] = n * nscale;
+    for (int k = D + 1; k < Dp; ++k) {
+        o[k] = 0.0;
+        if (orv) orv[k] = 0.0;
+    }
+}
+
+int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch, int len, int D, int Dp,
+                double c, double nscale, cudaStream_t st) {
+    const long rows = batch * len;
+    if (rows == 0) return SKB_OK;
+    const int tb = 128;
+    const unsigned grid = (unsigned)((rows + tb - 1) / tb);
+    if (dtype == SKB_F64)
+        prep_kernel<double><<<grid, tb, 0, st>>>((const double*)X, Xp, Xp_rev, batch, len, D, Dp, c, nscale);
+    else
+        prep_kernel<float><<<grid, tb, 0, st>>>((const float*)X, Xp, Xp_rev, batch, len, D, Dp, c, nscale);
+    return check_launch();
+}
+
+static int g_warps_per_sm = 0;
+void set_warps_per_sm(int w) { g_warps_per_sm = w; }
+int get_warps_per_sm() { return g_warps_per_sm; }
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Row width of prepped paths: 1 norm slot + D coordinates, rounded up to one of the widths the
+// fused kernels are specialised for (4, 6, 10 doubles), else to the next even number (generic loop).
+int padded_dim(int D) {
+    if (D + 1 <= 4) return 4;
+    if (D + 1 <= 6) return 6;
+    if (D + 1 <= 10) return 10;
+    return (D + 2) & ~1;
+}
+
+static int coarse_rows_per_lane(int M) {
+    int rc = (M + 31) / 32, rcp = 1;
+    while (rcp < rc) rcp <<= 1;
+    return rcp;
+}
+
+int solver_rows_per_lane(int M, int logd) {
+    const int rcp = coarse_rows_per_lane(M);
+    if (rcp > 8 || logd > 5 || (rcp << logd) > 32) return -1;
+    return rcp << logd;
+}
+
+int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st) {
+    if (solver_rows_per_lane(args.M, logd) < 0) return SKB_ERR_UNSUPPORTED;
+    const int rcp = coarse_rows_per_lane(args.M);
+    args.tstar = (args.M - 2) / rcp;
+    args.rcstar = (args.M - 2) % rcp;
+    args.pitch = 32L * (rcp << logd);
+    if (!args.counter) return SKB_ERR_WORKSPACE;
+    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    if (rc) return rc;
+    int dp2 = 0;
+    if (kind == KIND_RBF || kind == KIND_LINEAR) {
+        if (args.Dp == 4 || args.Dp == 6 || args.Dp == 10) dp2 = args.Dp / 2;
+    }
+    group_fn fn = nullptr;
+    const bool rbf = kind == KIND_RBF, lin = kind == KIND_LINEAR;
+    if (kind == KIND_STATIC || kind == KIND_INC) fn = launch_group_static;
+    else if (mode == 0) fn = rbf ? launch_group_fwd_rbf : (lin ? launch_group_fwd_lin : nullptr);
+    else if (mode == 1) fn = rbf ? launch_group_store_rbf : (lin ? launch_group_store_lin : nullptr);
+    else if (mode == 3) fn = rbf ? launch_group_rev_rbf : (lin ? launch_group_rev_lin : nullptr);
+    if (!fn) return SKB_ERR_UNSUPPORTED;
+    if (exact && (rbf || lin)) return SKB_ERR_UNSUPPORTED;
+    return fn(mode, kind, rcp, logd, dp2, exact, args, st);
+}
+
+}  // namespace skb

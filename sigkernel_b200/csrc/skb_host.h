@@ -5,29 +5,56 @@
 
 namespace skb {
 
-struct FwdArgs {
-    const double* Xp;   // prepped X rows [A*M][Dp]: (nx, c*x_0 .. c*x_{D-1}, 0 pad)
-    const double* Yp;   // prepped Y rows [B*N][Dp]: (ny,   y_0 ..   y_{D-1}, 0 pad)
-    const double* Ks;   // KIND_STATIC: coarse static matrix; KIND_INC: fine increments
-    double* out;
-    long njobs;
+// Arguments of solver_kernel (skb_solver.cuh).  Plain data, passed by value.
+struct KArgs {
+    const double* Xp;      // prepped X rows [A*M][Dp]: (nx, c*x_0 .. c*x_{D-1}, 0 pad); reversed copy in REV modes
+    const double* Yp;      // prepped Y rows [B*N][Dp]: (ny,   y_0 ..   y_{D-1}, 0 pad); reversed copy in REV modes
+    const double* Ks;      // KIND_STATIC: coarse static matrix; KIND_INC: fine increments
+    double* out;           // FWD modes: k(X_a, Y_b)
+    double* scratch;       // FWD_STORE writes / REV reads the forward grid: [job][q][pitch], behind a front pad
+    double* S;             // REV_S: coarse sensitivities (pairs, M-1, N-1)
+    double* grad;          // REV_GRAD: per-point gradients (pairs, M, D)
+    unsigned int* counter; // job queue (zeroed before the launch)
+    long job0;             // first job of this launch in the pair enumeration
+    long pitch;            // scratch row pitch in doubles (32 * R)
+    int njobs;             // jobs of this launch
     int A, B;
-    int M, N;           // production rows / columns per pair (nodes; KIND_INC: MM+1, NN+1)
-    int Mv, Nv;         // rows / columns actually stored in Ks
-    int Dp;             // doubles per prepped row (even)
-    int kind, pairs, s1;
-    int tstar, rcstar;  // lane / coarse row that ends up holding u[MM,NN]
-    double scale4;      // 4^-d (dyadic refinement: tile()/2^d twice, sigkernel.py:364)
+    int M, N;              // production rows / columns per pair (nodes; KIND_INC: MM+1, NN+1)
+    int Mv, Nv;            // rows / columns stored in Ks
+    int Dp, D;             // doubles per prepped row (even); path dimension
+    int pairs, s1;
+    int tstar, rcstar;     // lane / coarse row that ends up holding u[MM,NN]
+    double scale4;         // 4^-d (dyadic refinement: tile()/2^d twice, sigkernel.py:364)
+    double gscale;         // REV_GRAD: 2/sigma (RBF) or the linear scale factor
 };
-
-int launch_forward(FwdArgs args, int logd, bool exact, cudaStream_t st);
 
 // records the cudaError_t for skb_last_cuda_error(); returns SKB_OK or SKB_ERR_CUDA
 int check_cuda(cudaError_t e);
 inline int check_launch() { return check_cuda(cudaGetLastError()); }
 
 void set_warps_per_sm(int w);
-int launch_prep(const void* X, int dtype, double* Xp, long rows, int D, int Dp, double c, double nscale,
-                cudaStream_t st);
+int get_warps_per_sm();
+int sm_count();
+
+int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch, int len, int D, int Dp,
+                double c, double nscale, cudaStream_t st);
+
+// mode: MODE_* of skb_solver.cuh; kind: KIND_*; logd: dyadic order; dp2: Dp/2 specialisation (0 = generic).
+// Picks RC from args.M, fills tstar/rcstar, zeroes the job counter, launches.
+int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st);
+// rows-per-lane the dispatcher would use (needed to size the scratch pitch); <0 if unsupported
+int solver_rows_per_lane(int M, int logd);
+// padded row width the fused kinds are specialised for
+int padded_dim(int D);
+
+// per-group launchers (one translation unit each, to parallelise compilation)
+typedef int (*group_fn)(int mode, int kind, int rc, int logd, int dp2, bool exact, const KArgs&, cudaStream_t);
+int launch_group_fwd_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_fwd_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_static(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_store_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_store_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_rev_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+int launch_group_rev_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
 
 }  // namespace skb

@@ -1,0 +1,9 @@
+// skb_inst_rev_lin.cu -- instantiations of solver_kernel<MODE_REV_GRAD, KIND_LINEAR, ...> (one group per file: parallel build)
+#include "skb_launch.cuh"
+
+namespace skb {
+int launch_group_rev_lin(int mode, int kind, int rc, int logd, int dp2, bool exact, const KArgs& a, cudaStream_t st) {
+    (void)mode; (void)kind; (void)exact;
+    return launch_fused<MODE_REV_GRAD, KIND_LINEAR>(rc, logd, dp2, a, st);
+}
+}  // namespace skb

@@ -1,0 +1,460 @@
+// skb_solver.cuh -- the one kernel template behind every entry point of libsigkernel_b200.so.
+//
+// Replaces (reference crispitagorico/sigkernel @ 40a5831):
+//   sigkernel/cuda_backend.py:6-49, 121-160     sigkernel_cuda / sigkernel_Gram_cuda (one block per pair,
+//                                               one thread per grid row, global-memory anti-diagonals)
+//   sigkernel/static_kernels.py:17-33, 42-73    Linear / RBF static kernels
+//   sigkernel/sigkernel.py:362-364, 607-613     second difference + tile() (dyadic refinement)
+//   sigkernel/sigkernel.py:419-502, 256-343     prep_backward / _SigKernel.backward (reversed PDE,
+//                                               GG = u * u_rev, per-point gradients)
+//
+// Design (DESIGN.md has the derivation, the roofline and the measurements):
+//   * one WARP solves one path pair at a time and STREAMS through pairs taken from an atomic queue;
+//   * lane t owns RC coarse rows = R = RC * 2^d fine rows of the PDE grid, held in registers;
+//   * time advances in "macro steps" of one COARSE column (F = 2^d fine columns, fully unrolled);
+//     lane t runs one macro step behind lane t-1 (a skewed wavefront), so the only inter-lane traffic
+//     is the F bottom-row values of lane t-1 (shfl_up) and the static-kernel values of the first node
+//     row of lane t+1 (shfl_down), both produced at least one step EARLIER: every lane executes the
+//     same instruction stream, there is no shared-memory grid, no barrier;
+//   * the static kernel k(x_i, y_j) at node column e is evaluated by each lane for its own node rows
+//     three macro steps before the stencil consumes it (registers kh1..kh3): exp() and the L1 latency
+//     of the path loads overlap the dependent stencil chain of the same warp;
+//   * a lane that finishes a pair starts the next one in the following macro step: the 31-step
+//     wavefront ramp is paid once per warp, not once per pair.  Per pair there are N production steps
+//     but N-1 coarse columns; the odd step out (it would pair the last node column of one pair with
+//     the first of the next) re-arms the boundary u[., 0] = 1 -- in FMA mode for free, by running the
+//     stencil with coefficients (a, -b, const) = (0, 0, 1).
+//
+// MODE_FWD        out[pair] = u[MM, NN]
+// MODE_FWD_STORE  additionally stores u[p, q] (p < MM, q < NN) for the adjoint pass
+// MODE_REV_S      same sweep on the REVERSED paths (= the reference's flipped-increment solve,
+//                 sigkernel.py:438-469), multiplies by the stored forward grid and reduces to coarse
+//                 sensitivities S (plugin path: written out)
+// MODE_REV_GRAD   ... and contracts S with the analytic static-kernel derivative into per-point gradients
+//
+// fp64 throughout.  Per fine cell: 3 DP instructions (FMA form) or 4 (EXACT: reference rounding order).
+#pragma once
+#include "skb_common.cuh"
+#include "skb_host.h"
+
+namespace skb {
+
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3;
+
+// exp(x) for the RBF static kernel: x <= ~0 (|x - y|^2 >= 0 up to rounding), possibly hugely negative.
+// Same algorithm class as libdevice exp (Cody-Waite reduction by ln2, degree-11 polynomial, exponent
+// splice), without the branchy special-case handling: results below 2^-1000 flush to 0 (the reference's
+// torch.exp returns a denormal there; absolute difference < 1e-300).  Max error ~1 ulp like libdevice.
+__device__ __forceinline__ double exp_neg(double x) {
+    const double L2E = 1.4426950408889634e+0;
+    const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
+    const double LN2_HI = 6.9314718055994529e-1, LN2_LO = 2.3190468138462996e-17;
+    const double xc = fmax(x, -700.0);
+    const double t = fma(xc, L2E, MAGIC);
+    const double n = t - MAGIC;
+    double r = fma(n, -LN2_HI, xc);
+    r = fma(n, -LN2_LO, r);
+    double p = 2.5022322536502990e-8;                   // minimax coefficients used by libdevice's exp
+    p = fma(p, r, 2.7557249672502357e-7);
+    p = fma(p, r, 2.7557318923860444e-6);
+    p = fma(p, r, 2.4801587301428100e-5);
+    p = fma(p, r, 1.9841269841269841e-4);
+    p = fma(p, r, 1.3888888888885568e-3);
+    p = fma(p, r, 8.3333333333333800e-3);
+    p = fma(p, r, 4.1666666666666685e-2);
+    p = fma(p, r, 1.6666666666666666e-1);
+    p = fma(p, r, 5.0000000000000000e-1);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ni = __double2loint(t);                    // low word of t holds n (two's complement)
+    const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+    return x < -690.0 ? 0.0 : res;
+}
+
+__device__ __forceinline__ void job_decode(const KArgs& p, long j, int& a, int& b) {
+    if (p.pairs == PAIRS_GRAM) {
+        a = (int)(j / p.B);
+        b = (int)(j - (long)a * p.B);
+    } else if (p.pairs == PAIRS_BATCH) {
+        a = b = (int)j;
+    } else {  // upper triangle, row-major: row a holds (a,a) .. (a,A-1)
+        int r = 0;
+        long off = 0;
+        while (off + (p.A - r) <= j) { off += p.A - r; ++r; }
+        a = r;
+        b = r + (int)(j - off);
+    }
+}
+
+template <int MODE, int KIND, int RC, int LOGD, int DP2, bool EXACT, int MINB>
+__global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
+    constexpr int F = 1 << LOGD;   // fine columns per macro step
+    constexpr int R = RC * F;      // fine rows per lane
+    constexpr bool REV = (MODE == MODE_REV_S || MODE == MODE_REV_GRAD);
+    constexpr bool FUSED = (KIND == KIND_RBF || KIND == KIND_LINEAR);
+    constexpr bool VEC = (F >= 2);  // MM and R even: 16-byte aligned scratch rows
+    const int lane = threadIdx.x;
+    const int N = p.N, M = p.M;
+    const int NS = N < 3 ? 3 : N;  // macro steps per pair (N = 2 is padded with one idle production)
+    const int Dp = FUSED ? (DP2 > 0 ? 2 * DP2 : p.Dp) : 0;
+
+    extern __shared__ double smem[];   // MODE_REV_GRAD: accumulators [(rc*(D+1)+k)*32 + lane]
+
+    // ---- job stream state (per lane; lane t runs t steps behind lane 0) ----------------------------
+    int job = blockIdx.x;                   // production job (local index in [0, njobs))
+    int job_next = 0;                       // lane 0: prefetched next job
+    if (lane == 0) job_next = (int)(gridDim.x + atomicAdd(p.counter, 1u));
+    int a, b;                               // pair of the production stream
+    job_decode(p, p.job0 + job, a, b);
+    int sa = a, sb = b;                     // pair of the stencil stream (3 steps behind)
+    int sjob = job;
+    bool svalid = false;                    // stencil stream holds a real pair
+    bool pvalid = true;                     // production stream holds a real pair
+    int e = -lane;                          // production column; negative = lane not started
+    int c = NS - 3 - lane;                  // stencil column = e - 3 (mod NS); set properly below
+    while (c < 0) c += NS;                  // (value irrelevant until the first dummy step re-arms)
+
+    double u[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = 1.0;
+    double bots[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) bots[f] = 1.0;
+    double topprev = 1.0;
+    double kh1[RC], kh2[RC], kh3[RC];
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) kh1[rc] = kh2[rc] = kh3[rc] = 0.0;
+
+    // per-lane row offsets (clamped: values of clamped rows never reach a valid cell)
+    long xoff[RC];
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) {
+        int row = lane * RC + rc;
+        if (!FUSED) {
+            row = row < p.Mv ? row : p.Mv - 1;
+            if (REV) row = p.Mv - 1 - row;
+            xoff[rc] = (long)row * p.Nv;
+        } else {
+            row = row < M ? row : M - 1;
+            xoff[rc] = (long)row * Dp;     // REV: Xp already holds the reversed path
+        }
+    }
+    const double* xp[RC];
+    const double* yb = nullptr;
+    auto set_ptrs = [&]() {
+        const double* base;
+        if (FUSED) {
+            base = p.Xp + (long)a * M * Dp;
+            yb = p.Yp + (long)b * N * Dp;
+        } else {
+            const long pi = (p.pairs == PAIRS_BATCH) ? (long)a : (long)a * p.B + b;
+            base = p.Ks + pi * ((long)p.Mv * p.Nv);
+        }
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) xp[rc] = base + xoff[rc];
+    };
+    set_ptrs();
+    const double* syb = yb;                 // Y rows of the stencil stream's pair (REV_GRAD)
+    const double* sxb = FUSED ? p.Xp + (long)a * M * Dp : nullptr;
+
+    // REV: coarse sensitivities of this and the previous column; gradient accumulators in smem
+    double Sprev[RC];
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) Sprev[rc] = 0.0;
+    double Slast_cur = 0.0, Slast_prev = 0.0;   // lane's LAST coarse row at the two newest columns
+    const int D = p.D;
+    if (MODE == MODE_REV_GRAD) {
+        for (int i = 0; i < RC * (D + 1); ++i) smem[i * 32 + lane] = 0.0;
+    }
+
+    const double tw = p.s1 ? 0.0 : 1.0 / 12.0;
+    const int tstar = p.tstar, rcstar = p.rcstar;
+    const long NN = (long)(N - 1) << LOGD;
+
+#pragma unroll 1
+    while (true) {
+        // lanes still holding (or draining) a real pair keep the warp alive
+        const bool alive = pvalid || svalid;
+        if (!__any_sync(FULL, alive)) break;
+
+        // ---- 1. exchange values produced in EARLIER macro steps -----------------------------------
+        double tops[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const double t = shfl_up1(bots[f]);
+            tops[f] = lane == 0 ? 1.0 : t;              // grid row 0 is the boundary u = 1
+        }
+        const double bk_c = shfl_down1(kh2[0]);         // lane+1 first node row, node column c   (its kh2)
+        const double bk_c1 = shfl_down1(kh1[0]);        // lane+1 first node row, node column c+1 (its kh1)
+        const int na = __shfl_up_sync(FULL, a, 1);      // the pair lane-1 is producing for
+        const int nb_ = __shfl_up_sync(FULL, b, 1);
+        const int njob = __shfl_up_sync(FULL, job, 1);
+        const bool npv = __shfl_up_sync(FULL, (int)pvalid, 1) != 0;
+        double up_c = 0.0, up_c1 = 0.0;                 // REV: S of lane-1's last coarse row
+        if (REV) {
+            up_c = shfl_up1(Slast_cur);
+            up_c1 = shfl_up1(Slast_prev);
+            if (lane == 0) { up_c = 0.0; up_c1 = 0.0; }
+        }
+
+        // ---- 2. produce the static kernel at node column `col` for this lane's node rows ----------
+        const int col = e < 0 ? 0 : (e < N ? e : N - 1);
+        double knew[RC];
+        if (FUSED) {
+            const double* yp = yb + (long)col * Dp;
+            if (DP2 > 0) {
+                double2 yv[DP2 > 0 ? DP2 : 1];
+#pragma unroll
+                for (int i = 0; i < DP2; ++i) yv[i] = ldg2(yp + 2 * i);
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc) {
+                    double2 xv = ldg2(xp[rc]);
+                    double acc = fma(xv.y, yv[0].y, xv.x + yv[0].x);
+#pragma unroll
+                    for (int i = 1; i < DP2; ++i) {
+                        xv = ldg2(xp[rc] + 2 * i);
+                        acc = fma(xv.y, yv[i].y, fma(xv.x, yv[i].x, acc));
+                    }
+                    knew[rc] = acc;
+                }
+            } else {
+                double2 yv = ldg2(yp);
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc) {
+                    const double2 xv = ldg2(xp[rc]);
+                    knew[rc] = fma(xv.y, yv.y, xv.x + yv.x);
+                }
+#pragma unroll 1
+                for (int i = 2; i < Dp; i += 2) {
+                    yv = ldg2(yp + i);
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) {
+                        const double2 xv = ldg2(xp[rc] + i);
+                        knew[rc] = fma(xv.y, yv.y, fma(xv.x, yv.x, knew[rc]));
+                    }
+                }
+            }
+            if (KIND == KIND_RBF) {
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc) knew[rc] = exp_neg(knew[rc]);
+            }
+        } else {
+            int cc = col < p.Nv ? col : p.Nv - 1;
+            if (REV) cc = p.Nv - 1 - cc;
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) knew[rc] = __ldg(xp[rc] + cc);
+        }
+
+        // ---- 3. stencil coefficients of coarse column c (node columns c: kh3, c+1: kh2) ------------
+        const bool dummy = c >= N - 1;                   // no such coarse column: re-arm the boundary
+        double ca[RC], cb[RC];                           // FMA mode: cb holds -b
+        double cst = 0.0;
+        {
+            const double m = dummy ? 0.0 : 1.0;
+            const double hm = 0.5 * m, tm = tw * m;
+            if (!EXACT) cst = 1.0 - m;
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                double g;
+                if (KIND == KIND_INC) {
+                    g = kh3[rc];
+                } else {
+                    const double k00 = kh3[rc], k01 = kh2[rc];
+                    const double k10 = rc + 1 < RC ? kh3[rc + 1 < RC ? rc + 1 : rc] : bk_c;
+                    const double k11 = rc + 1 < RC ? kh2[rc + 1 < RC ? rc + 1 : rc] : bk_c1;
+                    // ((K[i+1,j+1] + K[i,j]) - K[i+1,j]) - K[i,j+1]  (sigkernel.py:363), then / 4^d.
+                    // In the reversed sweep (k00 <-> K[i+1,j+1] ...) the two subtractions swap so that
+                    // the rounding sequence of the ORIGINAL cell is reproduced.
+                    if (EXACT) {
+                        g = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(k11, k00), -k10), -k01), p.scale4);
+                    } else if (REV) {
+                        g = (((k11 + k00) - k01) - k10) * p.scale4;
+                    } else {
+                        g = (((k11 + k00) - k10) - k01) * p.scale4;
+                    }
+                }
+                if (EXACT) {
+                    coeffs<true>(g, p.s1 != 0, ca[rc], cb[rc]);
+                } else {
+                    // a = m (1 + g/2 + g^2/12), -b = m (g^2/12 - 1); m = 0 on the dummy step
+                    const double gg = g * g;
+                    ca[rc] = fma(gg, tm, fma(g, hm, m));
+                    cb[rc] = fma(gg, tm, -m);
+                }
+            }
+        }
+
+        // ---- 4. the stencil: R rows x F fine columns, all in registers -----------------------------
+        const bool real_col = svalid && !dummy;
+        double sacc[RC];
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) sacc[rc] = 0.0;
+        double* srow = nullptr;   // scratch row of fine column q = c*F (+f), this lane's first row
+        if (MODE == MODE_FWD_STORE) {
+            srow = p.scratch + (((long)sjob * NN + (long)c * F) * p.pitch + (long)lane * R);
+        } else if (REV) {
+            // reversed coordinates: p = MM-1-(lane*R + r), q = NN-1-(c*F + f)
+            const long MMl = (long)(M - 1) << LOGD;
+            srow = p.scratch + (((long)sjob * NN + (NN - 1 - (long)c * F)) * p.pitch + (MMl - (long)(lane + 1) * R));
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            double up = tops[f];
+            double diag = f == 0 ? topprev : tops[f == 0 ? 0 : f - 1];
+            double fw[R];   // REV: forward values u[p, q] of this column (reversed row order)
+#pragma unroll
+            for (int r = 0; r < R; ++r) fw[r] = 0.0;
+            if (REV && real_col) {
+                const double* src = srow - (long)f * p.pitch;
+                if (VEC) {
+#pragma unroll
+                    for (int r2 = 0; r2 < R / 2; ++r2) {
+                        const double2 v = *reinterpret_cast<const double2*>(src + 2 * r2);
+                        fw[R - 1 - 2 * r2] = v.x;
+                        fw[R - 2 - 2 * r2 >= 0 ? R - 2 - 2 * r2 : 0] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) fw[r] = src[R - 1 - r];
+                }
+            }
+            double dg[R];   // FWD_STORE: u[p, q] = the diagonal input of cell (p, q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double left = u[r];
+                double v;
+                if (EXACT) v = cell<true>(left, up, diag, ca[r >> LOGD], cb[r >> LOGD]);
+                else v = fma(ca[r >> LOGD], up, fma(ca[r >> LOGD], left, fma(cb[r >> LOGD], diag, cst)));
+                if (MODE == MODE_FWD_STORE) dg[r] = diag;
+                if (REV) sacc[r >> LOGD] = fma(fw[r], diag, sacc[r >> LOGD]);
+                diag = left;
+                up = v;
+                u[r] = v;
+            }
+            bots[f] = up;
+            if (MODE == MODE_FWD_STORE) {
+                if (real_col) {
+                    double* dst = srow + (long)f * p.pitch;
+                    if (VEC) {
+#pragma unroll
+                        for (int r2 = 0; r2 < R / 2; ++r2)
+                            *reinterpret_cast<double2*>(dst + 2 * r2) = make_double2(dg[2 * r2], dg[2 * r2 + 1 < R ? 2 * r2 + 1 : 0]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) dst[r] = dg[r];
+                    }
+                }
+            }
+        }
+        topprev = tops[F - 1];
+        if (EXACT) {
+            if (dummy) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) u[r] = 1.0;
+            }
+        }
+        if (dummy) topprev = 1.0;
+
+        // ---- 5. outputs ---------------------------------------------------------------------------
+        if (MODE == MODE_FWD || MODE == MODE_FWD_STORE) {
+            if (svalid && c == N - 2 && lane == tstar) {
+                double res = 0.0;
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc)
+                    if (rc == rcstar) res = u[(rc + 1) * F - 1];
+                if (p.pairs == PAIRS_BATCH) {
+                    p.out[sa] = res;
+                } else {
+                    p.out[(long)sa * p.B + sb] = res;
+                    if (p.pairs == PAIRS_SYM) p.out[(long)sb * p.B + sa] = res;
+                }
+            }
+        }
+        if (REV) {
+            // coarse sensitivities of column c (0 on the dummy step and for padded coarse rows)
+            double Scur[RC];
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                const bool ok = !dummy && (lane * RC + rc < M - 1);
+                Scur[rc] = ok ? sacc[rc] * p.scale4 : 0.0;
+            }
+            if (MODE == MODE_REV_S) {
+                if (real_col) {
+                    const long pi = (p.pairs == PAIRS_BATCH) ? (long)sa : (long)sa * p.B + sb;
+                    double* Sp = p.S + pi * ((long)(M - 1) * (N - 1));
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) {
+                        const int ip = lane * RC + rc;                   // reversed coarse row
+                        if (ip < M - 1) Sp[(long)(M - 2 - ip) * (N - 1) + (N - 2 - c)] = Scur[rc];
+                    }
+                }
+            } else {
+                // T[n', c] = S'[n', c] - S'[n'-1, c] - S'[n', c-1] + S'[n'-1, c-1]; W = T * k[n', c]
+                const double* yrow = syb + (long)(c < N ? c : N - 1) * Dp;
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc) {
+                    const double uc = rc > 0 ? Scur[rc > 0 ? rc - 1 : 0] : up_c;
+                    const double uc1 = rc > 0 ? Sprev[rc > 0 ? rc - 1 : 0] : up_c1;
+                    const double T = (Scur[rc] - uc) - (Sprev[rc] - uc1);
+                    const double W = KIND == KIND_RBF ? T * kh3[rc] : T;
+                    double* acc = smem + (rc * (D + 1)) * 32 + lane;
+                    acc[0] += W;
+                    for (int k = 0; k < D; ++k) acc[(k + 1) * 32] = fma(W, __ldg(yrow + 1 + k), acc[(k + 1) * 32]);
+                }
+                if (c == N - 1) {
+                    // the pair is complete for this lane: emit its node rows, clear the accumulators
+                    const long pi = (p.pairs == PAIRS_BATCH) ? (long)sa : (long)sa * p.B + sb;
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) {
+                        const int np = lane * RC + rc;                   // reversed node row
+                        double* acc = smem + (rc * (D + 1)) * 32 + lane;
+                        if (svalid && np < M) {
+                            double* gout = p.grad + (pi * M + (M - 1 - np)) * D;
+                            const double* xr = sxb + (long)np * Dp;
+                            const double sW = acc[0];
+                            for (int k = 0; k < D; ++k) {
+                                const double gy = acc[(k + 1) * 32];
+                                gout[k] = KIND == KIND_RBF ? fma(p.gscale, gy, -(__ldg(xr + 1 + k) * sW)) : p.gscale * gy;
+                            }
+                        }
+                        for (int k = 0; k <= D; ++k) acc[k * 32] = 0.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) Sprev[rc] = Scur[rc];
+            Slast_prev = Slast_cur;
+            Slast_cur = Scur[RC - 1];
+        }
+
+        // ---- 6. rotate the static-kernel history, advance both streams -----------------------------
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) { kh3[rc] = kh2[rc]; kh2[rc] = kh1[rc]; kh1[rc] = knew[rc]; }
+        if (c == NS - 1) {
+            // the stencil stream moves on to the pair the production stream is in (it switched
+            // exactly once during the last NS steps)
+            c = 0;
+            sa = a; sb = b; sjob = job; svalid = pvalid && e >= 0;
+            syb = yb;
+            if (FUSED) sxb = p.Xp + (long)a * M * Dp;
+        } else {
+            ++c;
+        }
+        if (++e == NS) {
+            e = 0;
+            if (lane == 0) {
+                job = job_next;
+                pvalid = job < p.njobs;
+                if (pvalid) {
+                    job_next = (int)(gridDim.x + atomicAdd(p.counter, 1u));
+                    job_decode(p, p.job0 + job, a, b);
+                }
+            } else {
+                job = njob; a = na; b = nb_; pvalid = npv;
+            }
+            if (pvalid) set_ptrs();
+        }
+    }
+}
+
+}  // namespace skb

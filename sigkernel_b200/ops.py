@@ -28,6 +28,14 @@ def _io(X, Y):
     return X.detach().contiguous(), Y.detach().contiguous(), (_lib.F64 if X.dtype == torch.float64 else _lib.F32)
 
 
+def _workspace(nbytes, device):
+    """Caller-owned scratch for one call (torch's caching allocator makes this cheap)."""
+    if nbytes == 0:
+        raise _lib.SigKernelB200Error("sigkernel_b200: shape not supported by this build "
+                                      "(needs ceil(len_x/32) * 2^dyadic_order <= 32)")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
 def _n_out(A, B, pairs):
     return A if pairs == "batch" else A * B
 
@@ -39,8 +47,7 @@ def sigkernel_forward(X, Y, static_kind, static_param, dyadic_order, pairs="gram
     B, N, _ = Yc.shape
     with torch.cuda.device(Xc.device):
         out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Xc.device)
-        nbytes = lib.skb_fwd_workspace_bytes(A, B, M, N, D)
-        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Xc.device)
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D), Xc.device)
         check(lib.skb_sigkernel_fwd(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
                                     _STATIC[static_kind], float(static_param),
                                     _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
@@ -61,10 +68,11 @@ def sigkernel_forward_from_static(Ks, dyadic_order, pairs="gram", naive=False, e
         A, B, M, N = Kc.shape
     with torch.cuda.device(Kc.device):
         out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Kc.device)
+        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(), Kc.device)
         check(lib.skb_sigkernel_fwd_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
                                                 _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
                                                 _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
-                                                out.data_ptr(), _stream()))
+                                                out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
     return out if pairs == "batch" else out.view(A, B)
 
 
@@ -78,10 +86,11 @@ def solve_increments(inc, naive=False, exact=True):
     P = ic.shape[0]
     with torch.cuda.device(ic.device):
         out = torch.empty(P, dtype=torch.float64, device=ic.device)
+        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(), ic.device)
         check(lib.skb_sigkernel_solve_increments(ic.data_ptr(), P, MM, NN,
                                                  _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
                                                  _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
-                                                 out.data_ptr(), _stream()))
+                                                 out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
     return out.view(lead)
 
 
@@ -94,8 +103,7 @@ def sigkernel_forward_backward(X, Y, static_kind, static_param, dyadic_order, pa
         n = _n_out(A, B, pairs)
         out = torch.empty(n, dtype=torch.float64, device=Xc.device)
         gp = torch.empty((n, M, D), dtype=torch.float64, device=Xc.device)
-        nbytes = lib.skb_bwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs])
-        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Xc.device)
+        ws, nbytes = _workspace(lib.skb_bwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
         check(lib.skb_sigkernel_fwd_bwd(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
                                         _STATIC[static_kind], float(static_param),
                                         _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
@@ -119,8 +127,7 @@ def sensitivity_from_static(Ks, dyadic_order, pairs="gram", naive=False):
         n = _n_out(A, B, pairs)
         out = torch.empty(n, dtype=torch.float64, device=Kc.device)
         S = torch.empty((n, M - 1, N - 1), dtype=torch.float64, device=Kc.device)
-        nbytes = lib.skb_bwd_workspace_bytes(A, B, M, N, 1, int(dyadic_order), _PAIRS[pairs])
-        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=Kc.device)
+        ws, nbytes = _workspace(lib.skb_bwd_workspace_bytes(A, B, M, N, 1, int(dyadic_order), _PAIRS[pairs]), Kc.device)
         check(lib.skb_sigkernel_sensitivity_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
                                                         _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
                                                         _PAIRS[pairs], out.data_ptr(), S.data_ptr(),

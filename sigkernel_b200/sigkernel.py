@@ -97,7 +97,8 @@ class _SigKernelGram(torch.autograd.Function):
             kind, param, _ = spec
             if need_grad:
                 # like the reference, the whole backward is computed eagerly (sigkernel.py:397-399)
-                G, gp = ops.sigkernel_forward_backward(X, Y, kind, param, dyadic_order, pairs, _naive_solver)
+                # (a symmetric Gram still needs d k(X_a, X_b) / d X_a for every ordered pair)
+                G, gp = ops.sigkernel_forward_backward(X, Y, kind, param, dyadic_order, "gram", _naive_solver)
             else:
                 G = ops.sigkernel_forward(X, Y, kind, param, dyadic_order, pairs, _naive_solver)
         else:
