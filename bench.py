@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- Gram path-pairs/sec (fp64) of the signature-kernel solver.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; N>1 under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path, host cores)
+
+Workload = BASELINE.json configs[2] (the headline): compute_Gram 128x128, len 64, dim 5, dyadic_order 2,
+RBFKernel(sigma=0.5), fp64, synthetic torch.rand paths (README recipe of the reference).  A step is one
+pass of the hot path over one batch: the whole Gram matrix.  At N>1 the X batch axis is sharded (weak
+scaling: every rank owns 128 rows of X, Y is replicated, one NCCL all-gather reassembles G).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(name="cfg3", A=128, B=128, L=64, D=5, d=2, sigma=0.5)
+WORKLOAD = ("compute_Gram 128x128 len=64 dim=5 dyadic_order=2 RBFKernel(sigma=0.5) fp64 "
+            "(BASELINE.json configs[2], headline)")
+METRIC = "gram_path_pairs_per_sec_fp64"
+UNIT = "pairs/s"
+
+
+def make_inputs(rank, torch):
+    """README recipe of the reference (README.md:57-59): seeded torch.rand on the CPU."""
+    gy = torch.Generator().manual_seed(0)
+    gx = torch.Generator().manual_seed(1000 + rank)
+    X = torch.rand((CFG["A"], CFG["L"], CFG["D"]), dtype=torch.float64, generator=gx)
+    Y = torch.rand((CFG["B"], CFG["L"], CFG["D"]), dtype=torch.float64, generator=gy)
+    return X, Y
+
+
+# DP instructions the algorithm needs per pair in this formulation (DESIGN.md "Roofline"):
+#   3 per fine cell (DFMA x3), 8 per coarse cell (second difference 3 + scale 1 + g^2 1 + a 2 + b 1),
+#   per node: D+1 for the dot product (+ norms) and 16 for exp (range reduction 4, polynomial 11, clamp 1)
+def dp_instr_per_pair(L, D, d, rbf=True):
+    MM = (L - 1) << d
+    return 3 * MM * MM + 8 * (L - 1) * (L - 1) + ((D + 1) + (16 if rbf else 0)) * L * L
+
+
+def stencil_dp_instr_per_pair(L, d):
+    MM = (L - 1) << d
+    return 3 * MM * MM
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [ln.split(",") for ts, ln in self.lines if t0 <= ts <= t1 + 0.1] or \
+               [ln.split(",") for ts, ln in self.lines]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# the reference arm and the CPU baseline: the reference's own CPU algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------
+def _cpu_gram_rows(args):
+    """One worker: Gram rows [lo, hi) of the workload through the oracle (the reference's compiled
+    Cython solver when oracle/_ref is present, else the C restatement)."""
+    lo, hi, rank_seed = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import sigkernel_oracle as O
+    X, Y = make_inputs(rank_seed, torch)
+    backend = "ref" if O.ref_backend() is not None else "c"
+    out = []
+    for r0 in range(lo, hi, 4):                       # 4 rows x 128 columns at a time: ~0.5 GB of grids
+        r1 = min(hi, r0 + 4)
+        out.append(O.compute_Gram(X[r0:r1], Y, O.RBFKernel(CFG["sigma"]), CFG["d"], backend=backend))
+    return torch.cat(out).sum().item()
+
+
+def cpu_gram_throughput(rows, workers):
+    """pairs/s of the CPU path on `rows` rows of X (x all 128 columns) using `workers` processes."""
+    import multiprocessing as mp
+    from oracle import sigkernel_oracle as O
+    kind = "reference" if O.ref_backend() is not None else "port"
+    workers = max(1, min(workers, rows))
+    bounds = [(rows * w // workers, rows * (w + 1) // workers, 0) for w in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        _cpu_gram_rows(bounds[0])
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            pool.map(_cpu_gram_rows, bounds)
+    dt = time.perf_counter() - t0
+    return rows * CFG["B"] / dt, dt, kind, workers
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    # bound the sample: ~2 rows per core (a row = 128 pairs ~ 0.2 s of one core), at most the full 128 rows
+    rows = min(CFG["A"], max(4, 2 * cores))
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt, kind, workers = cpu_gram_throughput(rows, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    value = rows * CFG["B"] / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{rows} rows of X x 128 columns = {rows * CFG['B']} pairs per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
+                         "sample": f"{rows}x128 pairs per step, {workers} processes (one row block each), "
+                                   "static kernel + tile + Cython/C solve exactly as the reference's CPU branch"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def measure_fp64_peak(skb, torch):
+    """thread-level DP instructions / s of a register-resident DADD / DMUL / DFMA chain (burst)."""
+    lib = skb._lib.lib
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rates = {}
+    for name, op in (("dfma", 0), ("dadd", 1), ("dmul", 2)):
+        best = 1e30
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            skb._lib.check(lib.skb_fp64_probe(op, sms * 8, 256, 40000, sink.data_ptr(), st))
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        rates[name] = sms * 8 * 256 * 40000 * 16 / (best * 1e-3)
+    return rates
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sigkernel_b200 as skb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A, B, L, D, d = CFG["A"], CFG["B"], CFG["L"], CFG["D"], CFG["d"]
+    Xh, Yh = make_inputs(rank, torch)
+    Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
+    Xd, Yd = Xh.to(dev), Yh.to(dev)
+    sk = skb.SigKernel(skb.RBFKernel(CFG["sigma"]), d)
+    G_all = torch.empty((world * A, B), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    Gh = torch.empty((world * A, B), dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        G = skb.ops.sigkernel_forward(Xd, Yd, "rbf", CFG["sigma"], d, "gram")
+        if world > 1:
+            dist.all_gather_into_tensor(G_all, G)
+            return G_all
+        return G
+
+    def step_e2e():
+        x = Xh.to(dev, non_blocking=True)
+        y = Yh.to(dev, non_blocking=True)
+        G = sk.compute_Gram(x, y)                      # the public, reference-shaped API
+        if world > 1:
+            dist.all_gather_into_tensor(G_all, G)
+            G = G_all
+        Gh.copy_(G, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return Gh
+
+    peak = measure_fp64_peak(skb, torch) if rank == 0 else None
+
+    # ---- kernel-resident throughput: `value` ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_k0.record(); ev_k1.record(); torch.cuda.synchronize()          # materialise the handles
+    skb._lib.lib.skb_set_profile_events(ev_k0.cuda_event, ev_k1.cuda_event)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    t_wall0 = time.perf_counter()
+    total_ms, kernel_ms = 0.0, 0.0
+    for _ in range(args.steps):
+        flush.zero_()                                   # evict L2 between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        kernel_ms += ev_k0.elapsed_time(ev_k1)
+    t_wall1 = time.perf_counter()
+    skb._lib.lib.skb_set_profile_events(None, None)
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    pairs_per_step = world * A * B
+    value = pairs_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers: `e2e` -------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t.item())
+    barrier()
+
+    if rank == 0:
+        k_ms = kernel_ms / args.steps
+        w_full = dp_instr_per_pair(L, D, d) * A * B            # per launch (one rank's kernel)
+        w_sten = stencil_dp_instr_per_pair(L, d) * A * B
+        peak_rate = max(peak["dadd"], peak["dmul"])
+        achieved = w_full / (k_ms * 1e-3)
+        prof = os.path.join(ROOT, "profiles", "r01_fwd_cfg3_summary.json")
+        traffic = None
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except (ValueError, OSError):
+                traffic = None
+        roofline = {
+            "bound": "fp64", "achieved": achieved / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
+            "frac": achieved / peak_rate, "traffic": traffic,
+            "kernel": "solver_kernel<FWD,RBF,RC=2,LOGD=2,DP2=3>", "kernel_ms": k_ms,
+            "peak_source": "measured live: register-resident DADD/DMUL chain (skb_fp64_probe); "
+                           "MEASURED_PEAKS.json has no fp64 entry",
+            "peak_dfma": peak["dfma"] / 1e12,
+            "achieved_stencil_only": w_sten / (k_ms * 1e-3) / 1e12,
+            "frac_stencil_only": w_sten / (k_ms * 1e-3) / peak_rate,
+            "dp_instr_per_pair": dp_instr_per_pair(L, D, d),
+            "hbm": {"algorithmic_bytes": 8 * (A * L * D + B * L * D + A * B),
+                    "achieved_GBps": 8 * (A * L * D + B * L * D + A * B) / (k_ms * 1e-3) / 1e9,
+                    "peak_GBps": _hbm_peak()},
+        }
+        cores = host_cores()
+        rows = 16 if cores < 8 else 32
+        try:
+            v_cpu, dt_cpu, kind, workers = cpu_gram_throughput(rows, 1)
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"{rows} rows of X x 128 columns = {rows * B} pairs in {dt_cpu:.1f} s; "
+                             "static kernel + tile (torch) + single-threaded Cython/C solve, as the reference's CPU branch"}
+        except Exception as exc:  # the oracle is test infrastructure; its absence must not kill the bench
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": A * B, "pairs_per_step": pairs_per_step,
+                       "sharding": "rows of X per rank, Y replicated, one all_gather_into_tensor of G" if world > 1 else "single GPU",
+                       "l2": "flushed (256 MiB memset) between timed iterations; inputs are 0.5 MB"},
+            "clocks": clocks,
+            "e2e": {"value": pairs_per_step * args.steps / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": Xh.numel() * 8 + Yh.numel() * 8, "d2h_bytes_per_step": Gh.numel() * 8,
+                    "ms_per_step": t_e2e / args.steps * 1e3,
+                    "api": "SigKernel(RBFKernel(0.5), 2).compute_Gram(X.cuda(), Y.cuda()) + .cpu()"},
+            "gpu_launches": 3 * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError, ValueError):
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

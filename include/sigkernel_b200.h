@@ -65,6 +65,12 @@ int         skb_version(void);             /* ABI version, bumped on any signatu
 /* Tuning knob (process-wide, default 0 = automatic): resident solver warps per SM. */
 void skb_set_warps_per_sm(int warps);
 
+/* Measurement hook (process-wide): when both are non-NULL, every solver launch records `start`
+ * immediately before and `stop` immediately after the solver kernel on the launch stream
+ * (cudaEvent_t passed as void*), so a caller can time the dominant kernel alone, without the
+ * path-preparation kernels around it.  Pass NULLs to disable. */
+void skb_set_profile_events(void* start_event, void* stop_event);
+
 /* Diagnostic used by bench.py for the roofline denominator: launches a register-resident chain of
  * fp64 instructions (op 0 = DFMA, 1 = DADD, 2 = DMUL); blocks*threads*iters*16 thread-level DP
  * instructions per launch, timed by the caller with CUDA events on `stream`.  threads <= 256. */

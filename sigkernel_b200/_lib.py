@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsigkernel_b200.so")
+# SIGKERNEL_B200_LIB overrides the library path (used by tuning experiments only)
+LIB_PATH = os.environ.get("SIGKERNEL_B200_LIB") or os.path.join(_HERE, "libsigkernel_b200.so")
 
 # enums of include/sigkernel_b200.h
 STATIC_LINEAR, STATIC_RBF = 0, 1
@@ -23,6 +24,7 @@ SYMBOLS = {
     "skb_last_cuda_error": (_i, []),
     "skb_version": (_i, []),
     "skb_set_warps_per_sm": (None, [_i]),
+    "skb_set_profile_events": (None, [_vp, _vp]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "skb_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _sz, _vp]),

@@ -92,6 +92,7 @@ const char* skb_error_string(int code) {
 int skb_last_cuda_error(void) { return g_last_cuda; }
 int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
+void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
 size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D) {
     if (A <= 0 || B <= 0 || M <= 0 || N <= 0 || D <= 0) return 0;

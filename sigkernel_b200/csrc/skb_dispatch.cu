@@ -45,6 +45,9 @@ int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch
     return check_launch();
 }
 
+static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+void set_profile_events(void* a, void* b) { g_ev_start = (cudaEvent_t)a; g_ev_stop = (cudaEvent_t)b; }
+
 static int g_warps_per_sm = 0;
 void set_warps_per_sm(int w) { g_warps_per_sm = w; }
 int get_warps_per_sm() { return g_warps_per_sm; }
@@ -102,7 +105,10 @@ int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStre
     else if (mode == 3) fn = rbf ? launch_group_rev_rbf : (lin ? launch_group_rev_lin : nullptr);
     if (!fn) return SKB_ERR_UNSUPPORTED;
     if (exact && (rbf || lin)) return SKB_ERR_UNSUPPORTED;
-    return fn(mode, kind, rcp, logd, dp2, exact, args, st);
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+    rc = fn(mode, kind, rcp, logd, dp2, exact, args, st);
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+    return rc;
 }
 
 }  // namespace skb

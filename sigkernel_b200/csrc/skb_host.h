@@ -33,6 +33,7 @@ int check_cuda(cudaError_t e);
 inline int check_launch() { return check_cuda(cudaGetLastError()); }
 
 void set_warps_per_sm(int w);
+void set_profile_events(void* start, void* stop);
 int get_warps_per_sm();
 int sm_count();
 

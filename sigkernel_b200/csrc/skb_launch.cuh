@@ -2,6 +2,10 @@
 #pragma once
 #include "skb_solver.cuh"
 
+#ifndef SKB_MINB_R8
+#define SKB_MINB_R8 20
+#endif
+
 namespace skb {
 
 template <int MODE, int R>
@@ -9,21 +13,23 @@ constexpr int minb_for() {
     // resident warps (= 1-warp blocks) per SM the register budget is sized for
     return (MODE == MODE_REV_S || MODE == MODE_REV_GRAD)
                ? (R <= 4 ? 16 : (R <= 8 ? 12 : (R <= 16 ? 8 : 6)))
-               : (R <= 8 ? 16 : (R <= 16 ? 12 : 8));
+               : (R <= 8 ? SKB_MINB_R8 : (R <= 16 ? 12 : 8));
 }
 
 template <int MODE, int KIND, int RC, int LOGD, int DP2, bool EXACT>
 int launch_one(const KArgs& a, cudaStream_t st) {
     constexpr int R = RC << LOGD;
     constexpr int MINB = minb_for<MODE, R>();
-    int wpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() : MINB;
+    // default: at most 16 resident warps per SM (measured: more adds nothing once the register file
+    // read ports are saturated, and fewer, longer-lived warps amortise the wavefront ramp better)
+    int wpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() : (MINB < 16 ? MINB : 16);
     if (wpsm > MINB) wpsm = MINB;
     long nw = (long)sm_count() * wpsm;
     if (nw > a.njobs) nw = a.njobs;
-    size_t smem = 0;
+    size_t smem = KIND == KIND_RBF ? EXP_TAB * sizeof(double) : 0;
     auto kern = solver_kernel<MODE, KIND, RC, LOGD, DP2, EXACT, MINB>;
     if (MODE == MODE_REV_GRAD) {
-        smem = (size_t)RC * (a.D + 1) * 32 * sizeof(double);
+        smem += (size_t)RC * (a.D + 1) * 32 * sizeof(double);
         if (smem > 200 * 1024) return SKB_ERR_UNSUPPORTED;
         if (smem > 48 * 1024) {
             int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

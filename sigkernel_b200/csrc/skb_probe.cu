@@ -27,6 +27,72 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed,
     if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
 }
 
+// operand-bandwidth variants: OP 3: v = fma(v, w, z) (three distinct register pairs per instruction),
+// OP 4: v = fma(v, w, b) (two distinct + one shared), OP 5: v = v + w (two distinct), OP 6: v = fma(a, v, z)
+template <int OP>
+__global__ void __launch_bounds__(256) fp64_probe3_kernel(int iters, double seed, double* sink) {
+    double v[8], w[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = seed + (double)(threadIdx.x + i) * 1e-9;
+        w[i] = 1.0 + seed * 1e-12 * (i + 1);
+        z[i] = seed * 1e-13 * (i + 1);
+    }
+    const double a = 1.0 + seed * 1e-12, b = seed * 1e-13;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (OP == 3) v[i] = fma(v[i], w[i], z[i]);
+                else if (OP == 4) v[i] = fma(v[i], w[i], b);
+                else if (OP == 5) v[i] = __dadd_rn(v[i], w[i]);
+                else v[i] = fma(a, v[i], z[i]);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i] + w[i] + z[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace skb
+
+namespace skb {
+// mixed-pipe variants: does integer work that fits in the free issue slots slow the fp64 stream down?
+// OP 7: 1 DADD (2 distinct) + 1 LOP3 (3 distinct 32-bit register operands) per pair of instructions
+// OP 8: 1 DADD + 2 LOP3   OP 9: 1 DADD + 1 IADD with an immediate (1 register operand)
+template <int OP>
+__global__ void __launch_bounds__(256) fp64_probe_mix_kernel(int iters, double seed, double* sink) {
+    double v[8], w[8];
+    unsigned a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        v[i] = seed + (double)(threadIdx.x + i) * 1e-9;
+        w[i] = seed * 1e-13 * (i + 1);
+        a[i] = threadIdx.x * 7 + i; b[i] = threadIdx.x * 13 + i; c[i] = threadIdx.x * 29 + i;
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = __dadd_rn(v[i], w[i]);
+                if (OP == 7 || OP == 8) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(a[i]) : "r"(b[i]), "r"(c[i]));
+                if (OP == 8) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(b[i]) : "r"(c[i]), "r"(a[i]));
+                if (OP == 9) asm volatile("add.u32 %0, %0, 3;" : "+r"(a[i]));
+            }
+        }
+    }
+    double s = 0.0;
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += v[i] + w[i]; t += a[i] + b[i] + c[i]; }
+    if (s == 123.456 || t == 0xdeadbeefu) sink[0] = s + t;
+}
 }  // namespace skb
 
 extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream) {
@@ -37,6 +103,13 @@ extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double
     if (op == 0) fp64_probe_kernel<0><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 1) fp64_probe_kernel<1><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 2) fp64_probe_kernel<2><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 3) fp64_probe3_kernel<3><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 4) fp64_probe3_kernel<4><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 5) fp64_probe3_kernel<5><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 6) fp64_probe3_kernel<6><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 7) fp64_probe_mix_kernel<7><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 8) fp64_probe_mix_kernel<8><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 9) fp64_probe_mix_kernel<9><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else return SKB_ERR_BAD_ENUM;
     return check_launch();
 }

@@ -22,8 +22,12 @@
 //   * a lane that finishes a pair starts the next one in the following macro step: the 31-step
 //     wavefront ramp is paid once per warp, not once per pair.  Per pair there are N production steps
 //     but N-1 coarse columns; the odd step out (it would pair the last node column of one pair with
-//     the first of the next) re-arms the boundary u[., 0] = 1 -- in FMA mode for free, by running the
-//     stencil with coefficients (a, -b, const) = (0, 0, 1).
+//     the first of the next) re-arms the boundary u[., 0] = 1 (by select, so that an overflowed pair
+//     cannot leak NaNs into the next one);
+//   * fp64 instructions on this part are paced by register-operand reads: DADD/DMUL issue every 2
+//     cycles per scheduler, a DFMA with three distinct register operands every 3 (measured with
+//     skb_fp64_probe ops 3-6).  The cell update is therefore written as DADD + DMUL + DFMA
+//     (u11 = a (u10 + u01) + (-b) u00: 7 operand-cycles) rather than three chained DFMAs (9).
 //
 // MODE_FWD        out[pair] = u[MM, NN]
 // MODE_FWD_STORE  additionally stores u[p, q] (p < MM, q < NN) for the adjoint pass
@@ -42,33 +46,36 @@ namespace skb {
 constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3;
 
 // exp(x) for the RBF static kernel: x <= ~0 (|x - y|^2 >= 0 up to rounding), possibly hugely negative.
-// Same algorithm class as libdevice exp (Cody-Waite reduction by ln2, degree-11 polynomial, exponent
-// splice), without the branchy special-case handling: results below 2^-1000 flush to 0 (the reference's
-// torch.exp returns a denormal there; absolute difference < 1e-300).  Max error ~1 ulp like libdevice.
-__device__ __forceinline__ double exp_neg(double x) {
-    const double L2E = 1.4426950408889634e+0;
-    const double MAGIC = 6755399441055744.0;           // 1.5 * 2^52
-    const double LN2_HI = 6.9314718055994529e-1, LN2_LO = 2.3190468138462996e-17;
-    const double xc = fmax(x, -700.0);
-    const double t = fma(xc, L2E, MAGIC);
-    const double n = t - MAGIC;
-    double r = fma(n, -LN2_HI, xc);
-    r = fma(n, -LN2_LO, r);
-    double p = 2.5022322536502990e-8;                   // minimax coefficients used by libdevice's exp
-    p = fma(p, r, 2.7557249672502357e-7);
-    p = fma(p, r, 2.7557318923860444e-6);
-    p = fma(p, r, 2.4801587301428100e-5);
-    p = fma(p, r, 1.9841269841269841e-4);
-    p = fma(p, r, 1.3888888888885568e-3);
-    p = fma(p, r, 8.3333333333333800e-3);
-    p = fma(p, r, 4.1666666666666685e-2);
-    p = fma(p, r, 1.6666666666666666e-1);
-    p = fma(p, r, 5.0000000000000000e-1);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int ni = __double2loint(t);                    // low word of t holds n (two's complement)
-    const double res = __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
-    return x < -690.0 ? 0.0 : res;
+// Table-driven: x = (256 n + j) ln2/256 + r, exp(x) = 2^n * T[j] * e^r with T[j] = 2^(j/256) in shared
+// memory and a degree-4 Taylor polynomial for |r| <= ln2/512 (truncation 4e-17 relative, <= 1 ulp
+// overall).  9 DP
+// instructions instead of libdevice's 16+; fp64 issue is the resource this kernel is bound by.
+// Results below e^-700 flush to 0 (torch.exp returns ~1e-304 there; absolute difference < 1e-300).
+constexpr int EXP_TAB = 256;
+__device__ __forceinline__ void exp_table_fill(double* tab, int lane) {
+    for (int j = lane; j < EXP_TAB; j += 32) tab[j] = exp2((double)j * (1.0 / EXP_TAB));
+    __syncwarp();
+}
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
+    const double K_L2E = 369.32993046757463;            // 256 / ln 2
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const double C_HI = 0x1.62e42fee00000p-9;           // ln2/256 = C_HI + C_LO; C_HI has 21 trailing zero bits,
+    const double C_LO = 0x1.a39ef35793c76p-41;          // so n * C_HI is exact for |256 n + j| < 2^21
+    const bool tiny = x < -700.0;
+    const double xc = tiny ? -700.0 : x;
+    const double t = fma(xc, K_L2E, MAGIC);
+    const double nf = t - MAGIC;
+    double r = fma(nf, -C_HI, xc);
+    r = fma(nf, -C_LO, r);
+    double q = fma(r, 4.1666666666666664e-2, 1.6666666666666666e-1);   // e^r - 1 = r (1 + r/2 + r^2/6 + r^3/24)
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    const int ti = __double2loint(t);                    // low word of t = 256 n + j (two's complement)
+    const double tj = tab[ti & (EXP_TAB - 1)];
+    const double v = fma(tj, q, tj);                     // <= 1 ulp overall (checked against libm)
+    const double res = __hiloint2double(__double2hiint(v) + ((ti >> 8) << 20), __double2loint(v));
+    return tiny ? 0.0 : res;
 }
 
 __device__ __forceinline__ void job_decode(const KArgs& p, long j, int& a, int& b) {
@@ -93,12 +100,17 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
     constexpr bool REV = (MODE == MODE_REV_S || MODE == MODE_REV_GRAD);
     constexpr bool FUSED = (KIND == KIND_RBF || KIND == KIND_LINEAR);
     constexpr bool VEC = (F >= 2);  // MM and R even: 16-byte aligned scratch rows
+    constexpr int UNR = (MODE == MODE_FWD && FUSED && R <= 16) ? 3 : 1;   // macro steps per loop trip
     const int lane = threadIdx.x;
     const int N = p.N, M = p.M;
     const int NS = N < 3 ? 3 : N;  // macro steps per pair (N = 2 is padded with one idle production)
     const int Dp = FUSED ? (DP2 > 0 ? 2 * DP2 : p.Dp) : 0;
 
-    extern __shared__ double smem[];   // MODE_REV_GRAD: accumulators [(rc*(D+1)+k)*32 + lane]
+    extern __shared__ double smem_raw[];
+    double* const etab = smem_raw;                                   // KIND_RBF: 2^(j/256) table
+    double* const smem = smem_raw + (KIND == KIND_RBF ? EXP_TAB : 0);  // MODE_REV_GRAD: accumulators
+                                                                     // [(rc*(D+1)+k)*32 + lane]
+    if (KIND == KIND_RBF) exp_table_fill(etab, threadIdx.x);
 
     // ---- job stream state (per lane; lane t runs t steps behind lane 0) ----------------------------
     int job = blockIdx.x;                   // production job (local index in [0, njobs))
@@ -126,7 +138,9 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
     for (int rc = 0; rc < RC; ++rc) kh1[rc] = kh2[rc] = kh3[rc] = 0.0;
 
     // per-lane row offsets (clamped: values of clamped rows never reach a valid cell)
+    // (fused kinds: 32-bit offsets in doubles -- the prepared paths are far below 16 GB)
     long xoff[RC];
+    unsigned xoff32[RC];
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) {
         int row = lane * RC + rc;
@@ -134,28 +148,32 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
             row = row < p.Mv ? row : p.Mv - 1;
             if (REV) row = p.Mv - 1 - row;
             xoff[rc] = (long)row * p.Nv;
+            xoff32[rc] = 0;
         } else {
             row = row < M ? row : M - 1;
-            xoff[rc] = (long)row * Dp;     // REV: Xp already holds the reversed path
+            xoff[rc] = 0;
+            xoff32[rc] = (unsigned)(row * Dp);     // REV: Xp already holds the reversed path
         }
     }
+    const unsigned xstride = (unsigned)(M * Dp), ystride = (unsigned)(N * Dp);
     const double* xp[RC];
     const double* yb = nullptr;
     auto set_ptrs = [&]() {
-        const double* base;
         if (FUSED) {
-            base = p.Xp + (long)a * M * Dp;
-            yb = p.Yp + (long)b * N * Dp;
+            const unsigned xb = (unsigned)a * xstride;
+            yb = p.Yp + (unsigned)b * ystride;
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) xp[rc] = p.Xp + (xb + xoff32[rc]);
         } else {
             const long pi = (p.pairs == PAIRS_BATCH) ? (long)a : (long)a * p.B + b;
-            base = p.Ks + pi * ((long)p.Mv * p.Nv);
-        }
+            const double* base = p.Ks + pi * ((long)p.Mv * p.Nv);
 #pragma unroll
-        for (int rc = 0; rc < RC; ++rc) xp[rc] = base + xoff[rc];
+            for (int rc = 0; rc < RC; ++rc) xp[rc] = base + xoff[rc];
+        }
     };
     set_ptrs();
     const double* syb = yb;                 // Y rows of the stencil stream's pair (REV_GRAD)
-    const double* sxb = FUSED ? p.Xp + (long)a * M * Dp : nullptr;
+    const double* sxb = FUSED ? p.Xp + (unsigned)a * xstride : nullptr;
 
     // REV: coarse sensitivities of this and the previous column; gradient accumulators in smem
     double Sprev[RC];
@@ -171,12 +189,10 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
     const int tstar = p.tstar, rcstar = p.rcstar;
     const long NN = (long)(N - 1) << LOGD;
 
-#pragma unroll 1
-    while (true) {
-        // lanes still holding (or draining) a real pair keep the warp alive
-        const bool alive = pvalid || svalid;
-        if (!__any_sync(FULL, alive)) break;
-
+    // One macro step.  The loop below runs UNR of them per trip so that the compiler can
+    // rename the loop-carried registers (static-kernel history, grid column) instead of moving them:
+    // register-file reads, moves included, are the resource this kernel is bound by.
+    auto step = [&]() __attribute__((always_inline)) {
         // ---- 1. exchange values produced in EARLIER macro steps -----------------------------------
         double tops[F];
 #pragma unroll
@@ -189,7 +205,6 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
         const int na = __shfl_up_sync(FULL, a, 1);      // the pair lane-1 is producing for
         const int nb_ = __shfl_up_sync(FULL, b, 1);
         const int njob = __shfl_up_sync(FULL, job, 1);
-        const bool npv = __shfl_up_sync(FULL, (int)pvalid, 1) != 0;
         double up_c = 0.0, up_c1 = 0.0;                 // REV: S of lane-1's last coarse row
         if (REV) {
             up_c = shfl_up1(Slast_cur);
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
             }
             if (KIND == KIND_RBF) {
 #pragma unroll
-                for (int rc = 0; rc < RC; ++rc) knew[rc] = exp_neg(knew[rc]);
+                for (int rc = 0; rc < RC; ++rc) knew[rc] = exp_neg(knew[rc], etab);
             }
         } else {
             int cc = col < p.Nv ? col : p.Nv - 1;
@@ -246,41 +261,36 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
         }
 
         // ---- 3. stencil coefficients of coarse column c (node columns c: kh3, c+1: kh2) ------------
+        // FMA mode holds (a, -b); both modes re-arm u = 1 on the dummy step by select (section 4).
         const bool dummy = c >= N - 1;                   // no such coarse column: re-arm the boundary
-        double ca[RC], cb[RC];                           // FMA mode: cb holds -b
-        double cst = 0.0;
-        {
-            const double m = dummy ? 0.0 : 1.0;
-            const double hm = 0.5 * m, tm = tw * m;
-            if (!EXACT) cst = 1.0 - m;
+        double ca[RC], cb[RC];
 #pragma unroll
-            for (int rc = 0; rc < RC; ++rc) {
-                double g;
-                if (KIND == KIND_INC) {
-                    g = kh3[rc];
-                } else {
-                    const double k00 = kh3[rc], k01 = kh2[rc];
-                    const double k10 = rc + 1 < RC ? kh3[rc + 1 < RC ? rc + 1 : rc] : bk_c;
-                    const double k11 = rc + 1 < RC ? kh2[rc + 1 < RC ? rc + 1 : rc] : bk_c1;
-                    // ((K[i+1,j+1] + K[i,j]) - K[i+1,j]) - K[i,j+1]  (sigkernel.py:363), then / 4^d.
-                    // In the reversed sweep (k00 <-> K[i+1,j+1] ...) the two subtractions swap so that
-                    // the rounding sequence of the ORIGINAL cell is reproduced.
-                    if (EXACT) {
-                        g = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(k11, k00), -k10), -k01), p.scale4);
-                    } else if (REV) {
-                        g = (((k11 + k00) - k01) - k10) * p.scale4;
-                    } else {
-                        g = (((k11 + k00) - k10) - k01) * p.scale4;
-                    }
-                }
+        for (int rc = 0; rc < RC; ++rc) {
+            double g;
+            if (KIND == KIND_INC) {
+                g = kh3[rc];
+            } else {
+                const double k00 = kh3[rc], k01 = kh2[rc];
+                const double k10 = rc + 1 < RC ? kh3[rc + 1 < RC ? rc + 1 : rc] : bk_c;
+                const double k11 = rc + 1 < RC ? kh2[rc + 1 < RC ? rc + 1 : rc] : bk_c1;
+                // ((K[i+1,j+1] + K[i,j]) - K[i+1,j]) - K[i,j+1]  (sigkernel.py:363), then / 4^d.
+                // In the reversed sweep (k00 <-> K[i+1,j+1] ...) the two subtractions swap so that
+                // the rounding sequence of the ORIGINAL cell is reproduced.
                 if (EXACT) {
-                    coeffs<true>(g, p.s1 != 0, ca[rc], cb[rc]);
+                    g = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(k11, k00), -k10), -k01), p.scale4);
+                } else if (REV) {
+                    g = (((k11 + k00) - k01) - k10) * p.scale4;
                 } else {
-                    // a = m (1 + g/2 + g^2/12), -b = m (g^2/12 - 1); m = 0 on the dummy step
-                    const double gg = g * g;
-                    ca[rc] = fma(gg, tm, fma(g, hm, m));
-                    cb[rc] = fma(gg, tm, -m);
+                    g = (((k11 + k00) - k10) - k01) * p.scale4;
                 }
+            }
+            if (EXACT) {
+                coeffs<true>(g, p.s1 != 0, ca[rc], cb[rc]);
+            } else {
+                // a = 1 + g/2 + g^2/12, -b = g^2/12 - 1  (tw = 0 for the S1 scheme)
+                const double gg = g * g;
+                ca[rc] = fma(gg, tw, fma(g, 0.5, 1.0));
+                cb[rc] = fma(gg, tw, -1.0);
             }
         }
 
@@ -297,63 +307,86 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
             const long MMl = (long)(M - 1) << LOGD;
             srow = p.scratch + (((long)sjob * NN + (NN - 1 - (long)c * F)) * p.pitch + (MMl - (long)(lane + 1) * R));
         }
+        // forward values u[p, q] of the cells this lane sweeps in this step (REV: reversed row order)
+        double fw[F][R];
+        if (REV) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-            double up = tops[f];
-            double diag = f == 0 ? topprev : tops[f == 0 ? 0 : f - 1];
-            double fw[R];   // REV: forward values u[p, q] of this column (reversed row order)
+            for (int f = 0; f < F; ++f) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) fw[r] = 0.0;
-            if (REV && real_col) {
-                const double* src = srow - (long)f * p.pitch;
-                if (VEC) {
-#pragma unroll
-                    for (int r2 = 0; r2 < R / 2; ++r2) {
-                        const double2 v = *reinterpret_cast<const double2*>(src + 2 * r2);
-                        fw[R - 1 - 2 * r2] = v.x;
-                        fw[R - 2 - 2 * r2 >= 0 ? R - 2 - 2 * r2 : 0] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) fw[r] = src[R - 1 - r];
-                }
-            }
-            double dg[R];   // FWD_STORE: u[p, q] = the diagonal input of cell (p, q)
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const double left = u[r];
-                double v;
-                if (EXACT) v = cell<true>(left, up, diag, ca[r >> LOGD], cb[r >> LOGD]);
-                else v = fma(ca[r >> LOGD], up, fma(ca[r >> LOGD], left, fma(cb[r >> LOGD], diag, cst)));
-                if (MODE == MODE_FWD_STORE) dg[r] = diag;
-                if (REV) sacc[r >> LOGD] = fma(fw[r], diag, sacc[r >> LOGD]);
-                diag = left;
-                up = v;
-                u[r] = v;
-            }
-            bots[f] = up;
-            if (MODE == MODE_FWD_STORE) {
+                for (int r = 0; r < R; ++r) fw[f][r] = 0.0;
                 if (real_col) {
-                    double* dst = srow + (long)f * p.pitch;
+                    const double* src = srow - (long)f * p.pitch;
                     if (VEC) {
 #pragma unroll
-                        for (int r2 = 0; r2 < R / 2; ++r2)
-                            *reinterpret_cast<double2*>(dst + 2 * r2) = make_double2(dg[2 * r2], dg[2 * r2 + 1 < R ? 2 * r2 + 1 : 0]);
+                        for (int r2 = 0; r2 < R / 2; ++r2) {
+                            const double2 v = *reinterpret_cast<const double2*>(src + 2 * r2);
+                            fw[f][R - 1 - 2 * r2] = v.x;
+                            fw[f][R - 2 - 2 * r2 >= 0 ? R - 2 - 2 * r2 : 0] = v.y;
+                        }
                     } else {
 #pragma unroll
-                        for (int r = 0; r < R; ++r) dst[r] = dg[r];
+                        for (int r = 0; r < R; ++r) fw[f][r] = src[R - 1 - r];
                     }
                 }
             }
         }
-        topprev = tops[F - 1];
-        if (EXACT) {
-            if (dummy) {
+        // Cells are visited in ANTI-DIAGONAL order inside the lane's R x F block: the cells of one
+        // anti-diagonal are independent (instruction-level parallelism inside one warp) and mostly
+        // share (a, -b), so consecutive DFMA/DMUL reuse their coefficient operand.
+        double U[R][F];
+        double sacc2[RC][F];
 #pragma unroll
-                for (int r = 0; r < R; ++r) u[r] = 1.0;
+        for (int rc = 0; rc < RC; ++rc)
+#pragma unroll
+            for (int f = 0; f < F; ++f) sacc2[rc][f] = 0.0;
+#pragma unroll
+        for (int dgl = 0; dgl < R + F - 1; ++dgl) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const int r = dgl - f;
+                if (r >= 0 && r < R) {
+                    const int rm = r > 0 ? r - 1 : 0, fm = f > 0 ? f - 1 : 0;
+                    const double left = f == 0 ? u[r] : U[r][fm];
+                    const double up = r == 0 ? tops[f] : U[rm][f];
+                    const double diag = r == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rm] : U[rm][fm]);
+                    double v;
+                    if (EXACT) v = cell<true>(left, up, diag, ca[r >> LOGD], cb[r >> LOGD]);
+                    else v = fma(ca[r >> LOGD], left + up, cb[r >> LOGD] * diag);   // cb holds -b
+                    if (REV) sacc2[r >> LOGD][f] = fma(fw[f][r], diag, sacc2[r >> LOGD][f]);
+                    U[r][f] = v;
+                    if (MODE == MODE_FWD_STORE) {
+                        // u[p, q] = the diagonal input of cell (p, q); stored as soon as it is known
+                        double* dst = srow + (long)f * p.pitch;
+                        if (VEC) {
+                            if (r & 1) {
+                                const int r2 = r - 1, r2m = r2 > 0 ? r2 - 1 : 0;
+                                const double dprev = r2 == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[r2m] : U[r2m][fm]);
+                                if (real_col) *reinterpret_cast<double2*>(dst + r2) = make_double2(dprev, diag);
+                            }
+                        } else {
+                            if (real_col) dst[r] = diag;
+                        }
+                    }
+                }
             }
         }
-        if (dummy) topprev = 1.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
+#pragma unroll
+        for (int f = 0; f < F; ++f) bots[f] = U[R - 1][f];
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+            double t = sacc2[rc][0];
+#pragma unroll
+            for (int f = 1; f < F; ++f) t += sacc2[rc][f];
+            sacc[rc] = t;
+        }
+        topprev = tops[F - 1];
+        if (dummy) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) u[r] = 1.0;
+            topprev = 1.0;
+        }
 
         // ---- 5. outputs ---------------------------------------------------------------------------
         if (MODE == MODE_FWD || MODE == MODE_FWD_STORE) {
@@ -436,7 +469,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
             c = 0;
             sa = a; sb = b; sjob = job; svalid = pvalid && e >= 0;
             syb = yb;
-            if (FUSED) sxb = p.Xp + (long)a * M * Dp;
+            if (FUSED) sxb = p.Xp + (unsigned)a * xstride;
         } else {
             ++c;
         }
@@ -450,10 +483,20 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
                     job_decode(p, p.job0 + job, a, b);
                 }
             } else {
-                job = njob; a = na; b = nb_; pvalid = npv;
+                job = njob; a = na; b = nb_; pvalid = njob < p.njobs;
             }
             if (pvalid) set_ptrs();
         }
+    };
+
+#pragma unroll 1
+    while (true) {
+        // lanes still holding (or draining) a real pair keep the warp alive; the extra steps a trip
+        // may run past the end are harmless (every output is guarded by the stream-valid flags)
+        const bool alive = pvalid || svalid;
+        if (!__any_sync(FULL, alive)) break;
+#pragma unroll
+        for (int it = 0; it < UNR; ++it) step();
     }
 }
 

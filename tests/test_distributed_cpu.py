@@ -1,0 +1,65 @@
+"""world_size-2 gloo tests (CPU) of the Gram sharding logic (sigkernel_b200/distributed.py): row blocks
+per rank, Y replicated, one all-gather -- with the solve injected (the oracle stands in for the kernel)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sigkernel_b200.distributed import row_block
+
+
+def test_row_block_partition():
+    for n in (1, 7, 8, 128, 513):
+        for w in (1, 2, 3, 8):
+            blocks = [row_block(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            sizes = [h - l for l, h in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, A, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import sigkernel_oracle as O
+        from sigkernel_b200.distributed import sharded_gram
+        g = torch.Generator().manual_seed(0)
+        X = torch.rand((A, 6, 2), dtype=torch.float64, generator=g)
+        Y = torch.rand((5, 7, 2), dtype=torch.float64, generator=g)
+        fn = lambda x, y: O.compute_Gram(x, y, O.RBFKernel(0.5), 1)
+        G = sharded_gram(X, Y, fn)
+        blk = sharded_gram(X, Y, fn, gather=False)
+        ref = fn(X, Y)
+        lo, hi = row_block(A, rank, world)
+        ok = torch.equal(G, ref) and torch.equal(blk, ref[lo:hi])
+        out_q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("A", [6, 7])
+def test_sharded_gram_world2_gloo(A):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, A, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res == {0: True, 1: True}

@@ -29,8 +29,8 @@ def measure(op, blocks, threads, iters, reps=5):
 def main():
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     out = {"gpu": torch.cuda.get_device_name(0), "sms": sms, "ops": {}}
-    for name, op in (("dfma", 0), ("dadd", 1), ("dmul", 2)):
-        for wpsm in (8, 16, 32, 64):
+    for name, op in (("dfma", 0), ("dadd", 1), ("dmul", 2), ("dfma_3distinct", 3), ("dfma_2distinct", 4), ("dadd_2distinct", 5), ("dfma_a_v_z", 6), ("dadd+lop3", 7), ("dadd+2lop3", 8), ("dadd+imad_imm", 9)):
+        for wpsm in (16, 64):
             blocks = sms * (wpsm * 32 // 256) if wpsm * 32 >= 256 else sms
             threads = 256 if wpsm * 32 >= 256 else wpsm * 32
             rate, ms = measure(op, blocks, threads, 200000)

@@ -31,7 +31,7 @@ def main():
         X = torch.rand((A, L, D), dtype=torch.float64, generator=g).cuda()
         Y = torch.rand((B, L, D), dtype=torch.float64, generator=g).cuda()
         for kind, par in (("rbf", 0.5), ("linear", 1.0)):
-            for w in (0, 4, 8, 12, 16):
+            for w in [int(x) for x in os.environ.get("SKB_WPSM", "0,8,12,16").split(",")]:
                 skb._lib.lib.skb_set_warps_per_sm(w)
                 best, med = time_it(lambda: skb.ops.sigkernel_forward(X, Y, kind, par, d, "gram"))
                 cells = A * B * ((L - 1) << d) ** 2
