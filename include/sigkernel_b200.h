@@ -79,9 +79,14 @@ int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, voi
 /* ---- workspaces -------------------------------------------------------------------
  * Every compute entry point takes a caller-owned device scratch buffer (256-byte aligned) that
  * holds the job-queue counter, the prepared paths and (backward) the forward solution grids.
- * The *_workspace_bytes functions return the size to allocate; 0 means bad arguments. */
-size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D);
-size_t skb_aux_workspace_bytes(void);   /* from_static / solve_increments */
+ * The *_workspace_bytes functions return the size to allocate; 0 means bad arguments.
+ * Shapes the register-resident kernels do not cover (ceil(M/32) rounded up to a power of two, times
+ * 2^dyadic_order, > 32) are served by a generic row-band sweep of the fine grid that needs a larger
+ * workspace (<= ~1 GiB; the pairs are processed in chunks that fit). */
+size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
+/* from_static (A,B,M,N as passed there) / solve_increments (A = B = P, M = MM+1, N = NN+1, dyadic_order 0,
+ * pairs = SKB_PAIRS_BATCH) */
+size_t skb_aux_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs);
 /* Recommended size for the backward entry points: room for the forward grids of all pairs,
  * capped at 8 GiB.  Any size >= the room for ONE pair's grid is accepted: the pairs are then
  * processed in chunks that fit. */

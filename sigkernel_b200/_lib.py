@@ -26,9 +26,9 @@ SYMBOLS = {
     "skb_set_warps_per_sm": (None, [_i]),
     "skb_set_profile_events": (None, [_vp, _vp]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
-    "skb_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "skb_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _sz, _vp]),
-    "skb_aux_workspace_bytes": (_sz, []),
+    "skb_aux_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd_from_static": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_sigkernel_solve_increments": (_i, [_vp, _l, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),

@@ -70,6 +70,87 @@ static KArgs base_args(int A, int B, int M, int N, int d, int scheme, int pairs)
     return a;
 }
 
+// ---- generic fallback (any len_x, len_y, dyadic order): coarse increments + row-band sweep ---------
+static const size_t kGenericBudget = (size_t)1 << 30;
+
+static size_t generic_doubles_per_job(int M, int N, int d, bool need_static) {
+    const size_t NNf = (size_t)(N - 1) << d;
+    return (need_static ? (size_t)M * N : 0) + (size_t)(M - 1) * (N - 1) + 2 * NNf;
+}
+
+static size_t generic_workspace_bytes(long njobs, int M, int N, int d, bool need_static) {
+    const size_t per = generic_doubles_per_job(M, N, d, need_static) * sizeof(double);
+    size_t jobs = (size_t)njobs;
+    size_t cap = kGenericBudget / per;
+    if (cap < 1) cap = 1;
+    if (jobs > cap) jobs = cap;
+    return align256(jobs * per) + 1024;
+}
+
+// src_kind: KIND_RBF / KIND_LINEAR (a.Xp / a.Yp prepared), KIND_STATIC (a.Ks = coarse static matrix) or
+// KIND_INC (a.Ks = fine increments, d must be 0).  a.M, a.N are the path lengths (KIND_INC: MM+1, NN+1).
+static int run_generic_forward(int src_kind, KArgs a, int d, bool exact, long njobs, char* scratch, size_t scratch_bytes,
+                               cudaStream_t st) {
+    const int M = a.M, N = a.N;
+    const long MMf = (long)(M - 1) << d, NNf = (long)(N - 1) << d;
+    if (MMf > 0x3fffffffL || NNf > 0x3fffffffL) return SKB_ERR_BAD_SHAPE;
+    const bool need_static = (src_kind == KIND_RBF || src_kind == KIND_LINEAR);
+    const bool need_inc = src_kind != KIND_INC;
+    const size_t per = generic_doubles_per_job(M, N, d, need_static) * sizeof(double);
+    if (scratch_bytes < per + 1024) return SKB_ERR_WORKSPACE;
+    long chunk = (long)((scratch_bytes - 1024) / per);
+    if (chunk > njobs) chunk = njobs;
+    int rcb = 1;
+    while (rcb < 8 && 32L * rcb < MMf + 1) rcb <<= 1;
+    const long H = 32L * rcb - 1;                         // fine rows per band
+    const long nbands = (MMf + H - 1) / H;
+    double* base = (double*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    for (long j0 = 0; j0 < njobs; j0 += chunk) {
+        const long nj = njobs - j0 < chunk ? njobs - j0 : chunk;
+        double* Ks = base;
+        double* incc = Ks + (need_static ? (size_t)nj * M * N : 0);
+        double* rowA = incc + (size_t)nj * (M - 1) * (N - 1);
+        double* rowB = rowA + (size_t)nj * NNf;
+        int rc;
+        const double* inc_src;
+        if (need_static) {
+            rc = launch_static_matrix(a, src_kind, j0, nj, Ks, st);
+            if (rc) return rc;
+            rc = launch_coarse_increments(Ks, incc, nj, M, N, a.scale4, exact, st);
+            if (rc) return rc;
+            inc_src = incc;
+        } else if (need_inc) {
+            rc = launch_coarse_increments(a.Ks + (size_t)j0 * M * N, incc, nj, M, N, a.scale4, exact, st);
+            if (rc) return rc;
+            inc_src = incc;
+        } else {
+            inc_src = a.Ks + (size_t)j0 * (M - 1) * (N - 1);
+        }
+        for (long band = 0; band < nbands; ++band) {
+            KArgs b = a;
+            const long row0 = band * H;
+            const long hb = MMf - row0 < H ? MMf - row0 : H;
+            b.Ks = inc_src;
+            b.Xp = b.Yp = nullptr;
+            b.M = (int)hb + 1;
+            b.N = (int)NNf + 1;
+            b.Mv = (int)MMf; b.Nv = (int)NNf;
+            b.Mc = M - 1; b.Nc = N - 1;
+            b.dshift = d;
+            b.band_row0 = (int)row0;
+            b.band_top = band > 0 ? ((band & 1) ? rowA : rowB) : nullptr;
+            b.band_bot = band + 1 < nbands ? ((band & 1) ? rowB : rowA) : nullptr;
+            b.out = band + 1 < nbands ? nullptr : a.out;
+            b.job0 = j0;
+            b.njobs = (int)nj;
+            b.scale4 = 1.0;
+            rc = launch_solver(MODE_FWD, KIND_INCV, 0, exact, b, st);
+            if (rc) return rc;
+        }
+    }
+    return SKB_OK;
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -94,13 +175,22 @@ int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
 void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
-size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D) {
-    if (A <= 0 || B <= 0 || M <= 0 || N <= 0 || D <= 0) return 0;
+size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return 0;
     const size_t Dp = (size_t)padded_dim(D);
-    return kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double));
+    size_t w = kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double));
+    if (solver_rows_per_lane(M, dyadic_order) < 0)
+        w += generic_workspace_bytes(njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM), M, N, dyadic_order, true);
+    return w;
 }
 
-size_t skb_aux_workspace_bytes(void) { return kCounterBytes; }
+size_t skb_aux_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || dyadic_order < 0 || dyadic_order > 20) return 0;
+    size_t w = kCounterBytes;
+    if (solver_rows_per_lane(M, dyadic_order) < 0)
+        w += generic_workspace_bytes(njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM), M, N, dyadic_order, false);
+    return w;
+}
 
 size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0) return 0;
@@ -127,7 +217,9 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
     if (arith != SKB_ARITH_FMA) return SKB_ERR_BAD_ENUM;
     if (!X || !Y || !out) return SKB_ERR_NULL;
-    if (!workspace || workspace_bytes < skb_fwd_workspace_bytes(A, B, M, N, D)) return SKB_ERR_WORKSPACE;
+    const size_t fixed_bytes = kCounterBytes + align256((size_t)A * M * padded_dim(D) * sizeof(double)) +
+                               align256((size_t)B * N * padded_dim(D) * sizeof(double));
+    if (!workspace || workspace_bytes < fixed_bytes) return SKB_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int Dp = padded_dim(D);
     char* w = (char*)workspace;
@@ -147,7 +239,13 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
     a.Dp = Dp; a.D = D;
-    return launch_solver(MODE_FWD, static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, dyadic_order, false, a, st);
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (solver_rows_per_lane(M, dyadic_order) >= 0) return launch_solver(MODE_FWD, kind, dyadic_order, false, a, st);
+    // shape outside the register-resident kernels: generic row-band fallback (a symmetric request is
+    // served by solving the full square)
+    if (pairs == SKB_PAIRS_SYM) a.pairs = SKB_PAIRS_GRAM;
+    return run_generic_forward(kind, a, dyadic_order, false, njobs_of(A, B, a.pairs), w + fixed_bytes,
+                               workspace_bytes - fixed_bytes, st);
 }
 
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order, int scheme,
@@ -162,7 +260,11 @@ int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, 
     const long nj = njobs_of(A, B, pairs);
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
-    return launch_solver(MODE_FWD, KIND_STATIC, dyadic_order, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
+    if (solver_rows_per_lane(M, dyadic_order) >= 0)
+        return launch_solver(MODE_FWD, KIND_STATIC, dyadic_order, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
+    if (pairs == SKB_PAIRS_SYM) a.pairs = SKB_PAIRS_GRAM;
+    return run_generic_forward(KIND_STATIC, a, dyadic_order, arith == SKB_ARITH_EXACT, njobs_of(A, B, a.pairs),
+                               (char*)workspace + kCounterBytes, workspace_bytes - kCounterBytes, (cudaStream_t)stream);
 }
 
 int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, int scheme, int arith,
@@ -176,7 +278,10 @@ int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, in
     a.Mv = MM; a.Nv = NN;
     a.Ks = inc; a.out = out; a.counter = (unsigned int*)workspace;
     a.njobs = (int)P;
-    return launch_solver(MODE_FWD, KIND_INC, 0, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
+    if (solver_rows_per_lane(MM + 1, 0) >= 0)
+        return launch_solver(MODE_FWD, KIND_INC, 0, arith == SKB_ARITH_EXACT, a, (cudaStream_t)stream);
+    return run_generic_forward(KIND_INC, a, 0, arith == SKB_ARITH_EXACT, P, (char*)workspace + kCounterBytes,
+                               workspace_bytes - kCounterBytes, (cudaStream_t)stream);
 }
 
 // shared driver of the two backward entry points: forward-with-store then reversed sweep, in chunks

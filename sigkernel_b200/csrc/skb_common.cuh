@@ -10,6 +10,8 @@ constexpr int KIND_LINEAR = 0;  // k = <x', y>
 constexpr int KIND_RBF = 1;     // k = exp(nx + ny + <x', y>)
 constexpr int KIND_STATIC = 2;  // k read from a caller-provided coarse static matrix
 constexpr int KIND_INC = 3;     // increments read directly (operator-level entry point)
+constexpr int KIND_INCV = 4;    // generic fallback: fine grid swept at LOGD = 0 in row bands, increments looked up
+                                // in a COARSE increment matrix (row >> d, col >> d)
 
 constexpr int PAIRS_GRAM = 0, PAIRS_BATCH = 1, PAIRS_SYM = 2;
 

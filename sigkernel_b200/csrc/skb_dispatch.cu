@@ -45,6 +45,60 @@ int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch
     return check_launch();
 }
 
+// ---- generic fallback helpers ---------------------------------------------------------------------
+// static matrix of the fused kinds for jobs [job0, job0 + njobs): Ks[local job][i][j] = k(x_i, y_j)
+// (libdevice exp here: this path is for shapes the fast kernels do not cover, not for speed)
+__global__ void static_matrix_kernel(const double* __restrict__ Xp, const double* __restrict__ Yp,
+                                     double* __restrict__ Ks, long job0, long njobs, int B, int M, int N,
+                                     int Dp, int rbf, int batch) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)M * N;
+    if (idx >= njobs * per) return;
+    const long jl = idx / per;
+    const int ij = (int)(idx - jl * per);
+    const int i = ij / N, j = ij - i * N;
+    const long pi = job0 + jl;
+    const long a = batch ? pi : pi / B, b = batch ? pi : pi - a * B;
+    const double* x = Xp + (a * M + i) * Dp;
+    const double* y = Yp + (b * N + j) * Dp;
+    double acc = x[0] + y[0];
+    for (int k = 1; k < Dp; ++k) acc = fma(x[k], y[k], acc);
+    Ks[idx] = rbf ? exp(acc) : acc;
+}
+
+// incc[job][i][j] = (((K[i+1,j+1] + K[i,j]) - K[i+1,j]) - K[i,j+1]) * 4^-d   (sigkernel.py:363-364)
+__global__ void coarse_inc_kernel(const double* __restrict__ Ks, double* __restrict__ incc, long pairs, int M,
+                                  int N, double scale4) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int Mc = M - 1, Nc = N - 1;
+    const long per = (long)Mc * Nc;
+    if (idx >= pairs * per) return;
+    const long p = idx / per;
+    const int ij = (int)(idx - p * per);
+    const int i = ij / Nc, j = ij - i * Nc;
+    const double* K = Ks + p * ((long)M * N);
+    const double k00 = K[(long)i * N + j], k01 = K[(long)i * N + j + 1];
+    const double k10 = K[(long)(i + 1) * N + j], k11 = K[(long)(i + 1) * N + j + 1];
+    incc[idx] = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(k11, k00), -k10), -k01), scale4);
+}
+
+int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double* Ks, cudaStream_t st) {
+    const long n = njobs * (long)a.M * a.N;
+    if (n == 0) return SKB_OK;
+    static_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.Xp, a.Yp, Ks, job0, njobs, a.B, a.M, a.N, a.Dp,
+                                                                      kind == KIND_RBF, a.pairs == PAIRS_BATCH);
+    return check_launch();
+}
+
+int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, int N, double scale4, bool exact,
+                             cudaStream_t st) {
+    (void)exact;   // the kernel always uses the reference's rounding sequence
+    const long n = pairs * (long)(M - 1) * (N - 1);
+    if (n == 0) return SKB_OK;
+    coarse_inc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Ks, incc, pairs, M, N, scale4);
+    return check_launch();
+}
+
 static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 void set_profile_events(void* a, void* b) { g_ev_start = (cudaEvent_t)a; g_ev_stop = (cudaEvent_t)b; }
 
@@ -85,6 +139,7 @@ int solver_rows_per_lane(int M, int logd) {
 }
 
 int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st) {
+    if (kind == KIND_INCV) logd = 0;   // the band sweep runs on the fine grid
     if (solver_rows_per_lane(args.M, logd) < 0) return SKB_ERR_UNSUPPORTED;
     const int rcp = coarse_rows_per_lane(args.M);
     args.tstar = (args.M - 2) / rcp;
@@ -99,7 +154,7 @@ int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStre
     }
     group_fn fn = nullptr;
     const bool rbf = kind == KIND_RBF, lin = kind == KIND_LINEAR;
-    if (kind == KIND_STATIC || kind == KIND_INC) fn = launch_group_static;
+    if (kind == KIND_STATIC || kind == KIND_INC || kind == KIND_INCV) fn = launch_group_static;
     else if (mode == 0) fn = rbf ? launch_group_fwd_rbf : (lin ? launch_group_fwd_lin : nullptr);
     else if (mode == 1) fn = rbf ? launch_group_store_rbf : (lin ? launch_group_store_lin : nullptr);
     else if (mode == 3) fn = rbf ? launch_group_rev_rbf : (lin ? launch_group_rev_lin : nullptr);

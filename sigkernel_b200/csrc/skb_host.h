@@ -24,6 +24,12 @@ struct KArgs {
     int Dp, D;             // doubles per prepped row (even); path dimension
     int pairs, s1;
     int tstar, rcstar;     // lane / coarse row that ends up holding u[MM,NN]
+    // KIND_INCV (generic row-band fallback): the launch sweeps fine rows [band_row0, band_row0 + M - 1)
+    const double* band_top; // u of the fine row above the band, per pair and fine column (NULL: boundary 1)
+    double* band_bot;       // receives u of the band's last fine row (NULL: last band)
+    int band_row0;          // first fine row of the band
+    int dshift;             // dyadic order (coarse index = fine index >> dshift)
+    int Mc, Nc;             // coarse increment matrix dims
     double scale4;         // 4^-d (dyadic refinement: tile()/2^d twice, sigkernel.py:364)
     double gscale;         // REV_GRAD: 2/sigma (RBF) or the linear scale factor
 };
@@ -45,6 +51,9 @@ int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch
 int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st);
 // rows-per-lane the dispatcher would use (needed to size the scratch pitch); <0 if unsupported
 int solver_rows_per_lane(int M, int logd);
+// generic fallback: coarse increments (pairs, M-1, N-1) from a static matrix; static matrix of the fused kinds
+int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, int N, double scale4, bool exact, cudaStream_t st);
+int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double* Ks, cudaStream_t st);
 // padded row width the fused kinds are specialised for
 int padded_dim(int D);
 

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
     constexpr int R = RC * F;      // fine rows per lane
     constexpr bool REV = (MODE == MODE_REV_S || MODE == MODE_REV_GRAD);
     constexpr bool FUSED = (KIND == KIND_RBF || KIND == KIND_LINEAR);
+    constexpr bool BAND = (KIND == KIND_INCV);   // row-band sweep of the fine grid (generic fallback)
     constexpr bool VEC = (F >= 2);  // MM and R even: 16-byte aligned scratch rows
     constexpr int UNR = (MODE == MODE_FWD && FUSED && R <= 16) ? 3 : 1;   // macro steps per loop trip
     const int lane = threadIdx.x;
@@ -144,7 +145,13 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) {
         int row = lane * RC + rc;
-        if (!FUSED) {
+        if (BAND) {
+            int frow = p.band_row0 + row;                      // global fine row
+            const int fmax = (p.Mc << p.dshift) - 1;
+            frow = frow < fmax ? frow : fmax;
+            xoff[rc] = (long)(frow >> p.dshift) * p.Nc;
+            xoff32[rc] = 0;
+        } else if (!FUSED) {
             row = row < p.Mv ? row : p.Mv - 1;
             if (REV) row = p.Mv - 1 - row;
             xoff[rc] = (long)row * p.Nv;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
             for (int rc = 0; rc < RC; ++rc) xp[rc] = p.Xp + (xb + xoff32[rc]);
         } else {
             const long pi = (p.pairs == PAIRS_BATCH) ? (long)a : (long)a * p.B + b;
-            const double* base = p.Ks + pi * ((long)p.Mv * p.Nv);
+            const double* base = p.Ks + (BAND ? (long)job * ((long)p.Mc * p.Nc) : pi * ((long)p.Mv * p.Nv));
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) xp[rc] = base + xoff[rc];
         }
@@ -199,6 +206,11 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
         for (int f = 0; f < F; ++f) {
             const double t = shfl_up1(bots[f]);
             tops[f] = lane == 0 ? 1.0 : t;              // grid row 0 is the boundary u = 1
+            if (BAND) {
+                // band > 0: the row above comes from the previous band's launch
+                if (lane == 0 && p.band_top != nullptr && svalid && c < N - 1)
+                    tops[f] = p.band_top[(long)sjob * (N - 1) + c];
+            }
         }
         const double bk_c = shfl_down1(kh2[0]);         // lane+1 first node row, node column c   (its kh2)
         const double bk_c1 = shfl_down1(kh1[0]);        // lane+1 first node row, node column c+1 (its kh1)
@@ -256,6 +268,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
         } else {
             int cc = col < p.Nv ? col : p.Nv - 1;
             if (REV) cc = p.Nv - 1 - cc;
+            if (BAND) cc >>= p.dshift;
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) knew[rc] = __ldg(xp[rc] + cc);
         }
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) {
             double g;
-            if (KIND == KIND_INC) {
+            if (KIND == KIND_INC || KIND == KIND_INCV) {
                 g = kh3[rc];
             } else {
                 const double k00 = kh3[rc], k01 = kh2[rc];
@@ -389,8 +402,17 @@ __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
         }
 
         // ---- 5. outputs ---------------------------------------------------------------------------
+        if (BAND) {
+            if (p.band_bot != nullptr && svalid && c < N - 1 && lane == tstar) {
+                double res = 0.0;
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc)
+                    if (rc == rcstar) res = u[(rc + 1) * F - 1];
+                p.band_bot[(long)sjob * (N - 1) + c] = res;
+            }
+        }
         if (MODE == MODE_FWD || MODE == MODE_FWD_STORE) {
-            if (svalid && c == N - 2 && lane == tstar) {
+            if (svalid && c == N - 2 && lane == tstar && (!BAND || p.out != nullptr)) {
                 double res = 0.0;
 #pragma unroll
                 for (int rc = 0; rc < RC; ++rc)

@@ -31,8 +31,8 @@ def _io(X, Y):
 def _workspace(nbytes, device):
     """Caller-owned scratch for one call (torch's caching allocator makes this cheap)."""
     if nbytes == 0:
-        raise _lib.SigKernelB200Error("sigkernel_b200: shape not supported by this build "
-                                      "(needs ceil(len_x/32) * 2^dyadic_order <= 32)")
+        raise _lib.SigKernelB200Error("sigkernel_b200: shape not supported by this entry point "
+                                      "(the backward needs ceil(len_x/32) * 2^dyadic_order <= 32)")
     return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
@@ -47,7 +47,7 @@ def sigkernel_forward(X, Y, static_kind, static_param, dyadic_order, pairs="gram
     B, N, _ = Yc.shape
     with torch.cuda.device(Xc.device):
         out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Xc.device)
-        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D), Xc.device)
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
         check(lib.skb_sigkernel_fwd(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
                                     _STATIC[static_kind], float(static_param),
                                     _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
@@ -68,7 +68,7 @@ def sigkernel_forward_from_static(Ks, dyadic_order, pairs="gram", naive=False, e
         A, B, M, N = Kc.shape
     with torch.cuda.device(Kc.device):
         out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Kc.device)
-        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(), Kc.device)
+        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(A, B, M, N, int(dyadic_order), _PAIRS[pairs]), Kc.device)
         check(lib.skb_sigkernel_fwd_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
                                                 _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
                                                 _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,
@@ -86,7 +86,7 @@ def solve_increments(inc, naive=False, exact=True):
     P = ic.shape[0]
     with torch.cuda.device(ic.device):
         out = torch.empty(P, dtype=torch.float64, device=ic.device)
-        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(), ic.device)
+        ws, nbytes = _workspace(lib.skb_aux_workspace_bytes(P, P, MM + 1, NN + 1, 0, _lib.PAIRS_BATCH), ic.device)
         check(lib.skb_sigkernel_solve_increments(ic.data_ptr(), P, MM, NN,
                                                  _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
                                                  _lib.ARITH_EXACT if exact else _lib.ARITH_FMA,

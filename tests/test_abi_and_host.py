@@ -58,15 +58,17 @@ def test_argument_validation_codes_without_gpu():
 
 def test_workspace_sizes():
     lib = skb._lib.lib
-    assert lib.skb_fwd_workspace_bytes(0, 1, 4, 4, 2) == 0
-    w = lib.skb_fwd_workspace_bytes(128, 128, 64, 64, 5)
+    assert lib.skb_fwd_workspace_bytes(0, 1, 4, 4, 2, 0, 0) == 0
+    w = lib.skb_fwd_workspace_bytes(128, 128, 64, 64, 5, 2, 0)
     assert w >= 2 * 128 * 64 * 6 * 8 and w % 256 == 0
     # backward: one padded forward grid per pair (row pitch 32 * rows-per-lane), capped at 8 GiB
     b = lib.skb_bwd_workspace_bytes(128, 128, 64, 64, 3, 1, 0)
     assert 128 * 128 * 126 * 128 * 8 <= b <= 128 * 128 * 126 * 128 * 8 + (1 << 22)
     assert lib.skb_bwd_workspace_bytes(512, 512, 128, 128, 8, 2, 0) <= (8 << 30) + (64 << 20)
     assert lib.skb_bwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) == 0        # unsupported shape says so
-    assert lib.skb_aux_workspace_bytes() >= 4
+    assert lib.skb_aux_workspace_bytes(2, 2, 8, 8, 1, 0) >= 4
+    # shapes outside the register-resident kernels get the generic row-band workspace
+    assert lib.skb_fwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) > lib.skb_fwd_workspace_bytes(2, 2, 200, 8, 2, 0, 0)
 
 
 def test_no_cpu_fallback():

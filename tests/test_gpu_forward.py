@@ -241,3 +241,44 @@ def test_many_pairs_stream_through_few_warps(skb, O):
     finally:
         skb._lib.lib.skb_set_warps_per_sm(0)
     assert fwd_err(got.cpu().numpy(), ref.numpy()) <= FWD_TOL
+
+
+# ---- shapes outside the register-resident kernels: generic row-band fallback ------------------------
+GENERIC_SHAPES = [
+    # A, B, M, N, D, d   (ceil(M/32) * 2^d > 32, or M > 256)
+    (2, 2, 300, 20, 2, 0),
+    (1, 2, 300, 9, 3, 1),
+    (2, 1, 10, 12, 2, 6),
+    (1, 1, 1000, 6, 2, 0),      # the reference's own limit is max(MM, NN) < 1024
+    (1, 2, 70, 150, 2, 3),
+    (2, 2, 40, 33, 4, 5),
+]
+
+
+@pytest.mark.parametrize("A,B,M,N,D,d", GENERIC_SHAPES)
+@pytest.mark.parametrize("static", ["rbf", "linear"])
+def test_generic_shapes_vs_oracle(skb, O, A, B, M, N, D, d, static):
+    X = make_paths("bm", 500 + M, (A, M, D))
+    Y = make_paths("bm", 600 + N, (B, N, D))
+    ref = O.compute_Gram(X, Y, O.RBFKernel(0.9) if static == "rbf" else O.LinearKernel(), d)
+    sk = skb.SigKernel(skb.RBFKernel(0.9) if static == "rbf" else skb.LinearKernel(), d)
+    got = sk.compute_Gram(X.cuda(), Y.cuda())
+    assert fwd_err(got.cpu().numpy(), ref.numpy()) <= FWD_TOL
+    if A == B:
+        refk = O.compute_kernel(X, Y, O.RBFKernel(0.9) if static == "rbf" else O.LinearKernel(), d)
+        assert fwd_err(sk.compute_kernel(X.cuda(), Y.cuda()).cpu().numpy(), refk.numpy()) <= FWD_TOL
+        if M == N:
+            assert fwd_err(sk.compute_Gram(X.cuda(), X.cuda(), sym=True).cpu().numpy(),
+                           O.compute_Gram(X, X, O.RBFKernel(0.9) if static == "rbf" else O.LinearKernel(), d).numpy()) <= FWD_TOL
+
+
+def test_generic_exact_bitwise(skb, O):
+    """The row-band fallback in exact arithmetic is still bit-identical to the reference solver."""
+    rng = np.random.default_rng(3)
+    inc = rng.uniform(-0.2, 0.2, size=(2, 700, 9))
+    ref = O.solve_batch(inc)[:, -1, -1]
+    assert np.array_equal(skb.ops.solve_increments(_dev(inc), exact=True).cpu().numpy(), ref)
+    X, Y = make_paths("rand", 5, (2, 290, 2)), make_paths("rand", 6, (2, 7, 2))
+    Ks = O.RBFKernel(0.5).Gram_matrix(X, Y)
+    ref = torch.from_numpy(O.solve_gram(O.increments(Ks, 1).numpy()))[:, :, -1, -1]
+    assert torch.equal(skb.ops.sigkernel_forward_from_static(Ks.cuda(), 1, "gram", exact=True).cpu(), ref)
