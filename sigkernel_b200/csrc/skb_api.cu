@@ -228,6 +228,9 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     double* Yp = (double*)(w + kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)));
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    const bool use5 = fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1);
+    if (use5 && kind == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on that path
     rc = launch_prep(X, io_dtype, Xp, nullptr, A, M, D, Dp, cx, nsc, st);
     if (rc) return rc;
     rc = launch_prep(Y, io_dtype, Yp, nullptr, B, N, D, Dp, 1.0, nsc, st);
@@ -239,7 +242,7 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
     a.Dp = Dp; a.D = D;
-    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (use5) return launch_forward5(kind, dyadic_order, a, st);
     if (solver_rows_per_lane(M, dyadic_order) >= 0) return launch_solver(MODE_FWD, kind, dyadic_order, false, a, st);
     // shape outside the register-resident kernels: generic row-band fallback (a symmetric request is
     // served by solving the full square)

@@ -1,4 +1,6 @@
 // skb_dispatch.cu -- path preparation kernel and the host-side dispatcher of solver_kernel.
+#include <math.h>
+#include <stdlib.h>
 #include "skb_common.cuh"
 #include "skb_host.h"
 
@@ -126,6 +128,8 @@ int padded_dim(int D) {
     return (D + 2) & ~1;
 }
 
+static double scale4_of_logd(int d) { return 1.0 / (double)(1ull << (2 * d)); }
+
 static int coarse_rows_per_lane(int M) {
     int rc = (M + 31) / 32, rcp = 1;
     while (rcp < rc) rcp <<= 1;
@@ -136,6 +140,52 @@ int solver_rows_per_lane(int M, int logd) {
     const int rcp = coarse_rows_per_lane(M);
     if (rcp > 8 || logd > 5 || (rcp << logd) > 32) return -1;
     return rcp << logd;
+}
+
+static bool use_fwd5() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("SKB_FWD5");      // development switch: SKB_FWD5=0 forces the v4 kernel
+        v = s ? atoi(s) : 1;
+    }
+    return v != 0;
+}
+
+// ---- fwd5: the forward-only kernel of the fused kinds (skb_fwd5.cuh) ---------------------------------
+double fwd5_kscale(int logd) { return scale4_of_logd(logd) / sqrt(12.0); }
+
+static bool fwd5_shape_ok(int rc, int logd) {   // SKB_FWD5_SHAPES of skb_fwd5.cuh
+    return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 2) || (rc == 4 && logd == 0);
+}
+
+bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
+    if (!use_fwd5() || s1 || N < 4) return false;
+    if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
+    if (solver_rows_per_lane(M, logd) < 0) return false;
+    const int Dp = padded_dim(D);
+    if (Dp != 4 && Dp != 6 && Dp != 10) return false;
+    return fwd5_shape_ok(coarse_rows_per_lane(M), logd);
+}
+
+int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
+    const int rcp = coarse_rows_per_lane(args.M);
+    args.tstar = (args.M - 2) / rcp;
+    args.rcstar = (args.M - 2) % rcp;
+    args.kscale = fwd5_kscale(logd);
+    args.sqrt3 = sqrt(3.0);
+    args.ek = 369.32993046757463;                 // 256 / ln 2
+    args.ehi = -0x1.62e42fee00000p-9;             // ln2/256 = hi + lo; hi has 21 trailing zero bits
+    args.elo = -0x1.a39ef35793c76p-41;
+    args.e4 = 1.0 / 24.0;
+    args.e3 = 1.0 / 6.0;
+    if (!args.counter) return SKB_ERR_WORKSPACE;
+    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    if (rc) return rc;
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+    rc = kind == KIND_RBF ? launch_group_fwd5_rbf(rcp, logd, args.Dp / 2, args, st)
+                          : launch_group_fwd5_lin(rcp, logd, args.Dp / 2, args, st);
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+    return rc;
 }
 
 int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st) {

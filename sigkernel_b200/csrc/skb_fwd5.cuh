@@ -1,0 +1,303 @@
+// skb_fwd5.cuh -- the forward-only kernel of the fused static kinds (Linear / RBF): the hot path of
+// compute_Gram / compute_kernel without gradients (BASELINE configs 2, 3, 5).
+//
+// Same decomposition as solver_kernel (skb_solver.cuh): one warp streams through path pairs, lane t owns
+// RC coarse rows (R = RC * 2^d fine rows in registers) and runs one macro step (= one coarse column)
+// behind lane t-1.  What is different -- every item below removes instructions, register-file reads or
+// exposed latency from the macro step, the three things the ncu source page of the v4 kernel showed it
+// to be bound by (profiles/r01_fwd_cfg3_*.json):
+//   * jobs are assigned statically (job = block + k * grid): every lane advances its own (a, b) with two
+//     adds and a carry when it wraps; no atomic queue, no per-step shuffles of the pair ids;
+//   * the lane's x rows live in registers for the whole pair (when RC * Dp <= 16 doubles) and the y row
+//     of the NEXT production column is loaded one macro step ahead: no load is consumed in the step
+//     that issued it (v4: 14 % of all stall samples were the first DADD after the loads);
+//   * the static kernel is kept as COLUMN DIFFERENCES d[i][j] = k[i][j+1] - k[i][j]; the increment of a
+//     coarse cell is g = d[i+1][j] - d[i][j], so one value (not two) comes from lane t+1 and a coarse cell
+//     costs 5 DP instructions instead of 8 (the dyadic scale 4^-d is folded into the polynomial
+//     coefficients c1 = 4^-d / 2, c2 = 16^-d / 12, constant-bank operands);
+//   * every shuffle is issued by the PRODUCER as soon as its source exists (the bottom-row value of fine
+//     column f right after its cell, the d history one step early), so a full macro step of independent
+//     work covers the SHFL latency instead of the first cells of the next step waiting on it;
+//   * production runs 4 columns ahead of the stencil (v4: 3) so that the shuffled d value is one step old;
+//   * the exp() underflow guard is one integer min on the high word instead of DSETP + 4 FSEL.
+//
+// fp64 throughout, FMA arithmetic (u11 = a (u10 + u01) + (-b) u00), results within 1e-13 of v4.
+// Reference semantics replaced: sigkernel/cuda_backend.py:121-160 (+ :6-49), static_kernels.py:17-33,
+// 42-73, sigkernel.py:362-364, 607-613 -- see skb_solver.cuh for the mapping.
+#pragma once
+#include "skb_solver.cuh"
+
+namespace skb {
+
+// (RC, LOGD) shapes fwd5 is instantiated for: the strips that fit 128 registers without spilling (16 resident
+// warps per SM); larger strips stay with solver_kernel.  Keep in sync with fwd5_shape_ok() (skb_dispatch.cu).
+#define SKB_FWD5_SHAPES(X) X(1, 0) X(1, 1) X(1, 2) X(1, 3) X(2, 0) X(2, 1) X(2, 2) X(4, 0)
+
+// exp(x) for x <= ~0, table-driven as exp_neg(); the underflow guard clamps x to >= -700.x through an
+// unsigned min on the high word (negative doubles order like their unsigned high words); NaN (canonical,
+// sign clear) passes through.
+__device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ tab, const KArgs& p) {
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const unsigned hi = min((unsigned)__double2hiint(x), 0xC085E000u);
+    const double xc = __hiloint2double((int)hi, __double2loint(x));
+    const double t = fma(xc, p.ek, MAGIC);               // ek = 256 / ln 2
+    const double nf = t - MAGIC;
+    double r = fma(nf, p.ehi, xc);                       // ehi + elo = -ln2 / 256; n * ehi is exact
+    r = fma(nf, p.elo, r);
+    double q = fma(r, p.e4, p.e3);                       // e^r - 1 = r (1 + r/2 + r^2/6 + r^3/24)
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    const int ti = __double2loint(t);                    // 256 n + j
+    const double tj = tab[ti & (EXP_TAB - 1)];
+    const double v = fma(tj, q, tj);
+    return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB - 1)) * 4096, __double2loint(v));
+}
+
+template <int KIND, int RC, int LOGD, int DP2, int MINB, int UNR>
+__global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
+    constexpr int F = 1 << LOGD;
+    constexpr int R = RC * F;
+    constexpr int Dp = 2 * DP2;
+    constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
+    constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
+    const int lane = threadIdx.x;
+    const int N = p.N, M = p.M;                  // N >= LEAD (the dispatcher sends shorter paths elsewhere)
+    const int G = gridDim.x;
+    const int first_job = blockIdx.x;
+
+    __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
+    __shared__ int4 ring_s[16];                  // job stream: (job, x offset, y offset, -) in doubles
+    if (KIND == KIND_RBF) {
+        for (int j = lane; j < EXP_TAB; j += 32) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
+    }
+
+    // ---- job stream -------------------------------------------------------------------------------
+    // Lane 0 takes jobs from an atomic queue (one pair ahead, so the atomic's latency is never waited for),
+    // decodes (a, b) and publishes (job, offset of X_a, offset of Y_b) in a 16-entry ring in shared memory;
+    // lane t picks entry w up when ITS production column wraps for the w-th time, t steps later (16 deep:
+    // lane 0 is at most 31 steps = 8 wraps ahead of lane 31 because N >= 4).  Until its first wrap lane
+    // t > 0 works on a "virtual" pair (the data of the first real pair, all outputs suppressed).
+    volatile int4* const ring = ring_s;
+    const unsigned xstride = (unsigned)(M * Dp), ystride = (unsigned)(N * Dp);
+    int job_next = 0;
+    unsigned xo, yo;                              // offsets (in doubles) of the production pair's paths
+    {
+        int a, b;
+        job_decode(p, p.job0 + first_job, a, b);
+        xo = (unsigned)a * xstride;
+        yo = (unsigned)b * ystride;
+        if (lane == 0) {
+            ring_s[0] = make_int4(first_job, (int)xo, (int)yo, 0);
+            job_next = (int)(G + atomicAdd(p.counter, 1u));
+        }
+    }
+    __syncwarp();
+    int c = (-lane - LEAD) % N;                   // stencil column; production column e = (c + LEAD) mod N
+    if (c < 0) c += N;
+    int w = lane == 0 ? 0 : -((lane - 1) / N + 1);   // index of the pair the production stream is in (< 0: virtual)
+    int pjob = lane == 0 ? first_job : -1;        // production stream's job (-1: virtual or past the end)
+    int sjob = -1;                                // stencil stream's job (-1: nothing to output)
+    bool done = false;
+    const int pc = (2 * N - 1 - LEAD) % N;        // stencil column at which the production column wraps
+    // this lane holds grid row MM-1 (the output) in u[(orc + 1) * F - 1] iff 0 <= orc < RC
+    const int orc = (M - 2) - lane * RC;
+
+    unsigned xoff[RC];
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) {
+        int row = lane * RC + rc;
+        row = row < M ? row : M - 1;              // clamped rows never reach a valid cell
+        xoff[rc] = (unsigned)(row * Dp);
+    }
+
+    double2 xr[XREG ? RC : 1][DP2];
+    const double* xb = p.Xp;
+    const double* yp = p.Yp;                      // y row of the NEXT production column
+    auto set_pair = [&]() {
+        xb = p.Xp + xo;
+        yp = p.Yp + yo;
+        if (XREG) {
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc)
+#pragma unroll
+                for (int i = 0; i < DP2; ++i) xr[rc][i] = ldg2(xb + xoff[rc] + 2 * i);
+        }
+    };
+    set_pair();
+    {
+        int e = c + LEAD;
+        e = e >= N ? e - N : e;
+        yp += (unsigned)(e * Dp);
+    }
+    double2 yq[DP2];
+#pragma unroll
+    for (int i = 0; i < DP2; ++i) yq[i] = ldg2(yp + 2 * i);
+
+    double u[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) u[r] = 1.0;
+    double tops[F];                               // row above the lane's strip, this step's fine columns
+#pragma unroll
+    for (int f = 0; f < F; ++f) tops[f] = 1.0;
+    double topprev = 1.0;
+    // static kernel, pre-scaled by kscale = 4^-d / sqrt(12): k at the newest column; column differences
+    // d[j] = k[j+1] - k[j] at the stencil columns c, c+1, c+2
+    double klast[RC], dA[RC], dB[RC], dC[RC];
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) klast[rc] = dA[rc] = dB[rc] = dC[rc] = 0.0;
+    double dn = 0.0;                              // d[c] of lane+1's first row
+
+    auto step = [&]() __attribute__((always_inline)) {
+        // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
+        // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
+        double ca[RC], cb[RC];
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+            const double el = (rc + 1 < RC ? dA[rc + 1 < RC ? rc + 1 : rc] : dn) - dA[rc];
+            cb[rc] = fma(el, el, -1.0);
+            ca[rc] = fma(el, p.sqrt3, cb[rc] + 2.0);
+        }
+
+        // ---- 2. the stencil: R rows x F fine columns in registers, anti-diagonal order ---------------
+        double U[R][F];
+        double tnext[F];
+#pragma unroll
+        for (int dgl = 0; dgl < R + F - 1; ++dgl) {
+            double ss[F], tt[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const int r = dgl - f;
+                if (r >= 0 && r < R) {
+                    const int rm = r > 0 ? r - 1 : 0, fm = f > 0 ? f - 1 : 0;
+                    const double left = f == 0 ? u[r] : U[r][fm];
+                    const double up = r == 0 ? tops[f] : U[rm][f];
+                    ss[f] = (f & 1) ? up + left : left + up;
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const int r = dgl - f;
+                if (r >= 0 && r < R) {
+                    const int rm = r > 0 ? r - 1 : 0, fm = f > 0 ? f - 1 : 0;
+                    const double diag = r == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rm] : U[rm][fm]);
+                    tt[f] = cb[r >> LOGD] * diag;
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const int r = dgl - f;
+                if (r >= 0 && r < R) {
+                    U[r][f] = fma(ca[r >> LOGD], ss[f], tt[f]);
+                    if (r == R - 1) {
+                        // hand the bottom-row value to lane+1 right away: it is consumed one step later
+                        const double t = shfl_up1(U[r][f]);
+                        tnext[f] = lane == 0 ? 1.0 : t;
+                    }
+                }
+            }
+        }
+        topprev = tops[F - 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
+#pragma unroll
+        for (int f = 0; f < F; ++f) tops[f] = tnext[f];
+
+        // ---- 3. production: static kernel at node column e = c + LEAD (y row loaded one step ago) -----
+        double dnew[RC];
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+            double2 xv = XREG ? xr[XREG ? rc : 0][0] : ldg2(xb + xoff[rc]);
+            double acc = fma(xv.y, yq[0].y, xv.x + yq[0].x);
+#pragma unroll
+            for (int i = 1; i < DP2; ++i) {
+                xv = XREG ? xr[XREG ? rc : 0][i] : ldg2(xb + xoff[rc] + 2 * i);
+                acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
+            }
+            if (KIND == KIND_RBF) acc = exp_neg5(acc, etab, p);
+            dnew[rc] = acc - klast[rc];
+            klast[rc] = acc;
+        }
+
+        // ---- 4. rotate the d history; ship lane+1's view of the next column ---------------------------
+        // next step's stencil column is c+1: it needs lane+1's d[c+1] = lane+1's dC as of NOW (made one
+        // step ago), so the shuffle does not wait for this step's production
+        dn = shfl_down1(dC[0]);
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) { dA[rc] = dB[rc]; dB[rc] = dC[rc]; dC[rc] = dnew[rc]; }
+
+        // ---- 5. advance; the rare events of a pair all hang off one test -------------------------------
+        // (a lane sees each event once per pair, but the lanes are skewed: the warp runs each block below
+        //  in about half of its steps, for one lane at a time -- they are kept as short as possible)
+        const int cc = c;
+        ++c;
+        yp += Dp;
+        if (cc >= N - 2 || cc == pc) {
+            if (cc == N - 2) {
+                // last coarse column done: u[MM, NN] is in the lane that owns grid row MM-1
+                if (sjob >= 0 && (unsigned)orc < (unsigned)RC) {
+                    double res = u[F - 1];
+#pragma unroll
+                    for (int rc = 1; rc < RC; ++rc)
+                        if (rc == orc) res = u[(rc + 1) * F - 1];
+                    if (p.pairs == PAIRS_SYM) {
+                        int a, b;
+                        job_decode(p, p.job0 + sjob, a, b);
+                        p.out[(long)a * p.B + b] = res;
+                        p.out[(long)b * p.B + a] = res;
+                    } else {
+                        p.out[p.job0 + sjob] = res;   // GRAM: job = a * B + b; BATCH: job = a
+                    }
+                }
+            }
+            if (cc == N - 1) {
+                // node column N-1 has no coarse column: the step computed garbage; re-arm the boundary
+                // u[., 0] = 1 and hand the stencil stream the pair the production stream is in
+#pragma unroll
+                for (int r = 0; r < R; ++r) u[r] = 1.0;
+                topprev = 1.0;
+                c = 0;
+                sjob = pjob;
+            }
+            if (cc == pc) {
+                // the production column wraps: next pair
+                ++w;
+                int4 ent = make_int4(-1, (int)xo, (int)yo, 0);
+                if (lane == 0) {
+                    int job = job_next;
+                    if (job < p.njobs) {
+                        job_next = (int)(G + atomicAdd(p.counter, 1u));
+                        int a, b;
+                        job_decode(p, p.job0 + job, a, b);
+                        ent.y = (int)((unsigned)a * xstride);
+                        ent.z = (int)((unsigned)b * ystride);
+                    } else {
+                        job = -1;
+                    }
+                    ent.x = job;
+                    ring_s[w & 15] = ent;
+                } else if (w >= 0) {
+                    const volatile int4* e = ring + (w & 15);
+                    ent.x = e->x; ent.y = e->y; ent.z = e->z;
+                }
+                pjob = ent.x;
+                if (w >= 0 && ent.x < 0) done = true;
+                xo = (unsigned)ent.y;
+                yo = (unsigned)ent.z;
+                set_pair();                       // virtual / past the end: the same pair's data again
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < DP2; ++i) yq[i] = ldg2(yp + 2 * i);
+    };
+
+#pragma unroll 1
+    while (true) {
+        const bool alive = !done || sjob >= 0;
+        if (!__any_sync(FULL, alive)) break;
+#pragma unroll
+        for (int it = 0; it < UNR; ++it) step();
+    }
+}
+
+}  // namespace skb

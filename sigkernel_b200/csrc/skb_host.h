@@ -32,6 +32,10 @@ struct KArgs {
     int Mc, Nc;             // coarse increment matrix dims
     double scale4;         // 4^-d (dyadic refinement: tile()/2^d twice, sigkernel.py:364)
     double gscale;         // REV_GRAD: 2/sigma (RBF) or the linear scale factor
+    // fwd5 (skb_fwd5.cuh): the static kernel is produced pre-scaled by kscale = 4^-d / sqrt(12); constants of
+    // the coefficient polynomial and of the table-driven exp live here so that they are constant-bank operands
+    double kscale, sqrt3;
+    double ek, ehi, elo, e4, e3;
 };
 
 // records the cudaError_t for skb_last_cuda_error(); returns SKB_OK or SKB_ERR_CUDA
@@ -66,5 +70,13 @@ int launch_group_store_rbf(int, int, int, int, int, bool, const KArgs&, cudaStre
 int launch_group_store_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
 int launch_group_rev_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
 int launch_group_rev_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
+// forward-only kernel of the fused kinds (skb_fwd5.cuh); SKB_ERR_UNSUPPORTED if the shape is not instantiated
+int launch_group_fwd5_rbf(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_lin(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+// true if skb_sigkernel_fwd should take the fwd5 path for this problem (scheme S2, N >= 4, shape instantiated)
+bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1);
+// scale the static kernel is produced with on the fwd5 path (Linear: folded into the prepared X rows)
+double fwd5_kscale(int logd);
+int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st);
 
 }  // namespace skb
