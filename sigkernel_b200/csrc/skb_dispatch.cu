@@ -158,19 +158,32 @@ static bool fwd5_shape_ok(int rc, int logd) {   // SKB_FWD5_SHAPES of skb_fwd5.c
     return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 2) || (rc == 4 && logd == 0);
 }
 
+// warps per pair fwd5 would use (1, 2 or 4: the smallest count whose per-lane strip is an instantiated
+// shape), and the coarse rows per lane that go with it; 0 if the shape is not covered
+static int fwd5_plan(int M, int logd, int* rc_out) {
+    for (int nw = 1; nw <= 4; nw *= 2) {
+        int rc = (M + 32 * nw - 1) / (32 * nw), rcp = 1;
+        while (rcp < rc) rcp <<= 1;
+        if (fwd5_shape_ok(rcp, logd)) {
+            if (rc_out) *rc_out = rcp;
+            return nw;
+        }
+    }
+    return 0;
+}
+
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     if (!use_fwd5() || s1 || N < 4) return false;
     if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
-    if (solver_rows_per_lane(M, logd) < 0) return false;
     const int Dp = padded_dim(D);
     if (Dp != 4 && Dp != 6 && Dp != 10) return false;
-    return fwd5_shape_ok(coarse_rows_per_lane(M), logd);
+    return fwd5_plan(M, logd, nullptr) > 0;
 }
 
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
-    const int rcp = coarse_rows_per_lane(args.M);
-    args.tstar = (args.M - 2) / rcp;
-    args.rcstar = (args.M - 2) % rcp;
+    int rcp = 0;
+    const int nw = fwd5_plan(args.M, logd, &rcp);
+    if (nw == 0) return SKB_ERR_UNSUPPORTED;
     args.kscale = fwd5_kscale(logd);
     args.sqrt3 = sqrt(3.0);
     args.ek = 369.32993046757463;                 // 256 / ln 2
@@ -182,8 +195,11 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
     int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;
     if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
-    rc = kind == KIND_RBF ? launch_group_fwd5_rbf(rcp, logd, args.Dp / 2, args, st)
-                          : launch_group_fwd5_lin(rcp, logd, args.Dp / 2, args, st);
+    typedef int (*fwd5_fn)(int, int, int, const KArgs&, cudaStream_t);
+    static const fwd5_fn table[2][3] = {
+        {launch_group_fwd5_lin_nw1, launch_group_fwd5_lin_nw2, launch_group_fwd5_lin_nw4},
+        {launch_group_fwd5_rbf_nw1, launch_group_fwd5_rbf_nw2, launch_group_fwd5_rbf_nw4}};
+    rc = table[kind == KIND_RBF ? 1 : 0][nw == 1 ? 0 : (nw == 2 ? 1 : 2)](rcp, logd, args.Dp / 2, args, st);
     if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return rc;
 }

@@ -54,30 +54,38 @@ __device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ 
     return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB - 1)) * 4096, __double2loint(v));
 }
 
-template <int KIND, int RC, int LOGD, int DP2, int MINB, int UNR>
-__global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
+// NW warps (32 NW lanes) share one pair: warp w+1 continues the wavefront of warp w (lane 0 of warp w+1 is
+// "lane 32 (w+1)"); the two values that cross the warp boundary every step (bottom row of lane 31 going down,
+// d of the next warp's first row going up) go through double-buffered shared memory and one block barrier.
+template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR>
+__global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int F = 1 << LOGD;
     constexpr int R = RC * F;
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
-    const int lane = threadIdx.x;
+    constexpr int RING = 64;                     // job ring depth (lane 0 is < 32 NW steps = RING/2 wraps ahead)
+    const int glane = threadIdx.x;               // position in the wavefront
+    const int lane = glane & 31;
+    const int wid = glane >> 5;
     const int N = p.N, M = p.M;                  // N >= LEAD (the dispatcher sends shorter paths elsewhere)
     const int G = gridDim.x;
     const int first_job = blockIdx.x;
 
     __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
-    __shared__ int4 ring_s[16];                  // job stream: (job, x offset, y offset, -) in doubles
+    __shared__ int4 ring_s[RING];                // job stream: (job, x offset, y offset, -) in doubles
+    __shared__ double xtop[NW][2][F];            // [warp][step parity]: bottom row of the warp above
+    __shared__ double xdn[NW][2];                // [warp][step parity]: d of this warp's first row, for the warp above
     if (KIND == KIND_RBF) {
-        for (int j = lane; j < EXP_TAB; j += 32) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
+        for (int j = glane; j < EXP_TAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
     }
 
     // ---- job stream -------------------------------------------------------------------------------
     // Lane 0 takes jobs from an atomic queue (one pair ahead, so the atomic's latency is never waited for),
-    // decodes (a, b) and publishes (job, offset of X_a, offset of Y_b) in a 16-entry ring in shared memory;
-    // lane t picks entry w up when ITS production column wraps for the w-th time, t steps later (16 deep:
-    // lane 0 is at most 31 steps = 8 wraps ahead of lane 31 because N >= 4).  Until its first wrap lane
-    // t > 0 works on a "virtual" pair (the data of the first real pair, all outputs suppressed).
+    // decodes (a, b) and publishes (job, offset of X_a, offset of Y_b) in a ring in shared memory; lane t
+    // picks entry w up when ITS production column wraps for the w-th time, t steps later (lane 0 is at most
+    // 32 NW - 1 steps, i.e. < RING/2 wraps, ahead of the last lane because N >= 4).  Until its first wrap
+    // lane t > 0 works on a "virtual" pair (the data of the first real pair, all outputs suppressed).
     volatile int4* const ring = ring_s;
     const unsigned xstride = (unsigned)(M * Dp), ystride = (unsigned)(N * Dp);
     int job_next = 0;
@@ -87,26 +95,26 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
         job_decode(p, p.job0 + first_job, a, b);
         xo = (unsigned)a * xstride;
         yo = (unsigned)b * ystride;
-        if (lane == 0) {
+        if (glane == 0) {
             ring_s[0] = make_int4(first_job, (int)xo, (int)yo, 0);
             job_next = (int)(G + atomicAdd(p.counter, 1u));
         }
     }
-    __syncwarp();
-    int c = (-lane - LEAD) % N;                   // stencil column; production column e = (c + LEAD) mod N
+    if (NW > 1) __syncthreads(); else __syncwarp();
+    int c = (-glane - LEAD) % N;                  // stencil column; production column e = (c + LEAD) mod N
     if (c < 0) c += N;
-    int w = lane == 0 ? 0 : -((lane - 1) / N + 1);   // index of the pair the production stream is in (< 0: virtual)
-    int pjob = lane == 0 ? first_job : -1;        // production stream's job (-1: virtual or past the end)
+    int w = glane == 0 ? 0 : -((glane - 1) / N + 1);   // index of the pair the production stream is in (< 0: virtual)
+    int pjob = glane == 0 ? first_job : -1;       // production stream's job (-1: virtual or past the end)
     int sjob = -1;                                // stencil stream's job (-1: nothing to output)
     bool done = false;
     const int pc = (2 * N - 1 - LEAD) % N;        // stencil column at which the production column wraps
     // this lane holds grid row MM-1 (the output) in u[(orc + 1) * F - 1] iff 0 <= orc < RC
-    const int orc = (M - 2) - lane * RC;
+    const int orc = (M - 2) - glane * RC;
 
     unsigned xoff[RC];
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) {
-        int row = lane * RC + rc;
+        int row = glane * RC + rc;
         row = row < M ? row : M - 1;              // clamped rows never reach a valid cell
         xoff[rc] = (unsigned)(row * Dp);
     }
@@ -147,8 +155,15 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) klast[rc] = dA[rc] = dB[rc] = dC[rc] = 0.0;
     double dn = 0.0;                              // d[c] of lane+1's first row
+    int par = 0;                                  // step parity (NW > 1: buffer of the cross-warp handoff)
 
+    // Cross-warp handoff (NW > 1): writes into the parity buffer, ONE block barrier per step, reads after it.
+    // (Split arrive/sync named barriers were measured slower than the plain barrier: 6.1 vs 4.65 ms at
+    // 64x512 pairs of len 128.)
     auto step = [&]() __attribute__((always_inline)) {
+        // next step's stencil column is c+1: the warp above needs this warp's first-row d[c+1] = dC as of NOW
+        // (made one step ago)
+        if (NW > 1 && lane == 0 && wid > 0) xdn[wid][par] = dC[0];
         // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
         // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
         double ca[RC], cb[RC];
@@ -191,8 +206,8 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
                     U[r][f] = fma(ca[r >> LOGD], ss[f], tt[f]);
                     if (r == R - 1) {
                         // hand the bottom-row value to lane+1 right away: it is consumed one step later
-                        const double t = shfl_up1(U[r][f]);
-                        tnext[f] = lane == 0 ? 1.0 : t;
+                        tnext[f] = shfl_up1(U[r][f]);
+                        if (NW > 1 && lane == 31 && wid + 1 < NW) xtop[wid + 1 < NW ? wid + 1 : 0][par][f] = U[r][f];
                     }
                 }
             }
@@ -200,8 +215,20 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
         topprev = tops[F - 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
+        // next step's stencil column is c+1: it needs lane+1's d[c+1] = lane+1's dC as of NOW (made one
+        // step ago), so this exchange does not wait for this step's production
+        dn = shfl_down1(dC[0]);
+        if (NW > 1) {
+            __syncthreads();
+            if (lane == 31 && wid + 1 < NW) dn = xdn[wid + 1 < NW ? wid + 1 : 0][par];
+        }
 #pragma unroll
-        for (int f = 0; f < F; ++f) tops[f] = tnext[f];
+        for (int f = 0; f < F; ++f) {
+            double tb = 1.0;                      // grid row 0 is the boundary u = 1
+            if (NW > 1 && lane == 0 && wid > 0) tb = xtop[wid][par][f];
+            tops[f] = lane == 0 ? tb : tnext[f];
+        }
+        par ^= 1;
 
         // ---- 3. production: static kernel at node column e = c + LEAD (y row loaded one step ago) -----
         double dnew[RC];
@@ -219,10 +246,7 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
             klast[rc] = acc;
         }
 
-        // ---- 4. rotate the d history; ship lane+1's view of the next column ---------------------------
-        // next step's stencil column is c+1: it needs lane+1's d[c+1] = lane+1's dC as of NOW (made one
-        // step ago), so the shuffle does not wait for this step's production
-        dn = shfl_down1(dC[0]);
+        // ---- 4. rotate the d history ---------------------------------------------------------------------
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) { dA[rc] = dB[rc]; dB[rc] = dC[rc]; dC[rc] = dnew[rc]; }
 
@@ -263,7 +287,7 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
                 // the production column wraps: next pair
                 ++w;
                 int4 ent = make_int4(-1, (int)xo, (int)yo, 0);
-                if (lane == 0) {
+                if (glane == 0) {
                     int job = job_next;
                     if (job < p.njobs) {
                         job_next = (int)(G + atomicAdd(p.counter, 1u));
@@ -275,9 +299,9 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
                         job = -1;
                     }
                     ent.x = job;
-                    ring_s[w & 15] = ent;
+                    ring_s[w & (RING - 1)] = ent;
                 } else if (w >= 0) {
-                    const volatile int4* e = ring + (w & 15);
+                    const volatile int4* e = ring + (w & (RING - 1));
                     ent.x = e->x; ent.y = e->y; ent.z = e->z;
                 }
                 pjob = ent.x;
@@ -294,7 +318,11 @@ __global__ void __launch_bounds__(32, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll 1
     while (true) {
         const bool alive = !done || sjob >= 0;
-        if (!__any_sync(FULL, alive)) break;
+        if (NW > 1) {
+            if (!__syncthreads_or(alive)) break;
+        } else {
+            if (!__any_sync(FULL, alive)) break;
+        }
 #pragma unroll
         for (int it = 0; it < UNR; ++it) step();
     }

@@ -71,8 +71,13 @@ int launch_group_store_lin(int, int, int, int, int, bool, const KArgs&, cudaStre
 int launch_group_rev_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
 int launch_group_rev_lin(int, int, int, int, int, bool, const KArgs&, cudaStream_t);
 // forward-only kernel of the fused kinds (skb_fwd5.cuh); SKB_ERR_UNSUPPORTED if the shape is not instantiated
-int launch_group_fwd5_rbf(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
-int launch_group_fwd5_lin(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+// (one translation unit per static kind and warps-per-pair count NW)
+int launch_group_fwd5_rbf_nw1(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_rbf_nw2(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_rbf_nw4(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_lin_nw1(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_lin_nw2(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_lin_nw4(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 // true if skb_sigkernel_fwd should take the fwd5 path for this problem (scheme S2, N >= 4, shape instantiated)
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1);
 // scale the static kernel is produced with on the fwd5 path (Linear: folded into the prepared X rows)
