@@ -39,13 +39,13 @@ def make_inputs(rank, torch):
     return X, Y
 
 
-# DP instructions the algorithm needs per pair in this formulation (DESIGN.md "Roofline"):
-#   3 per fine cell (DADD, DMUL, DFMA), 8 per coarse cell (second difference 3 + scale 1 + g^2 1 + a 2 + b 1),
-#   per node: D+1 for the dot product (+ norms) and 10 for the table-driven exp (clamp 1, reduction 4,
-#   polynomial 4, table multiply-add 1)
+# DP instructions the algorithm needs per pair in the formulation of skb_fwd5.cuh (DESIGN.md "Roofline"):
+#   3 per fine cell (DADD, DMUL, DFMA), 4 per coarse cell (increment 1, -b 1, a 2),
+#   per node: D+1 for the dot product (+ norms), 9 for the table-driven exp (reduction 4, polynomial 4,
+#   table multiply-add 1) and 1 for the column difference
 def dp_instr_per_pair(L, D, d, rbf=True):
     MM = (L - 1) << d
-    return 3 * MM * MM + 8 * (L - 1) * (L - 1) + ((D + 1) + (10 if rbf else 0)) * L * L
+    return 3 * MM * MM + 4 * (L - 1) * (L - 1) + ((D + 1) + 1 + (9 if rbf else 0)) * L * L
 
 
 def stencil_dp_instr_per_pair(L, d):
@@ -296,7 +296,7 @@ def run_ours(args):
         w_sten = stencil_dp_instr_per_pair(L, d) * A * B
         peak_rate = max(peak["dadd"], peak["dmul"])
         achieved = w_full / (k_ms * 1e-3)
-        prof = os.path.join(ROOT, "profiles", "r01_fwd_cfg3_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r01_fwd5_cfg3_summary.json")
         traffic = None
         if os.path.exists(prof):
             try:
@@ -306,12 +306,14 @@ def run_ours(args):
         roofline = {
             "bound": "fp64", "achieved": achieved / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
             "frac": achieved / peak_rate, "traffic": traffic,
-            "kernel": "solver_kernel<FWD,RBF,RC=2,LOGD=2,DP2=3>", "kernel_ms": k_ms,
+            "kernel": "fwd5_kernel<RBF,RC=2,LOGD=2,DP2=3,NW=1>", "kernel_ms": k_ms,
             "peak_source": "measured live: register-resident DADD/DMUL chain (skb_fp64_probe); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "peak_dfma": peak["dfma"] / 1e12,
             "achieved_stencil_only": w_sten / (k_ms * 1e-3) / 1e12,
             "frac_stencil_only": w_sten / (k_ms * 1e-3) / peak_rate,
+            # SURVEY.md 8(d)'s conservative accounting: 4 DP instructions per fine cell, nothing else
+            "frac_survey_4_per_cell": (4.0 / 3.0) * w_sten / (k_ms * 1e-3) / peak_rate,
             "dp_instr_per_pair": dp_instr_per_pair(L, D, d),
             "hbm": {"algorithmic_bytes": 8 * (A * L * D + B * L * D + A * B),
                     "achieved_GBps": 8 * (A * L * D + B * L * D + A * B) / (k_ms * 1e-3) / 1e9,

@@ -74,8 +74,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 
     __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
     __shared__ int4 ring_s[RING];                // job stream: (job, x offset, y offset, -) in doubles
-    __shared__ double xtop[NW][2][F];            // [warp][step parity]: bottom row of the warp above
-    __shared__ double xdn[NW][2];                // [warp][step parity]: d of this warp's first row, for the warp above
+    // Neighbour exchange through shared memory, double-buffered by step parity (one warp / block barrier per
+    // step separates the writes from the reads): lane g writes its bottom row to slot g+1 and reads the row
+    // above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0 needs no special case and a
+    // warp boundary (NW > 1) is just another slot; likewise the d value of the first node row goes UP one lane.
+    constexpr int H = (F + 1) / 2;
+    constexpr int NL = 32 * NW;
+    __shared__ double2 tx[2][H][NL + 1];
+    __shared__ double dx[2][NL + 1];
     if (KIND == KIND_RBF) {
         for (int j = glane; j < EXP_TAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
     }
@@ -96,6 +102,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         xo = (unsigned)a * xstride;
         yo = (unsigned)b * ystride;
         if (glane == 0) {
+            for (int q = 0; q < 2; ++q) {
+                for (int h = 0; h < H; ++h) tx[q][h][0] = make_double2(1.0, 1.0);
+                dx[q][NL] = 0.0;
+            }
             ring_s[0] = make_int4(first_job, (int)xo, (int)yo, 0);
             job_next = (int)(G + atomicAdd(p.counter, 1u));
         }
@@ -157,13 +167,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     double dn = 0.0;                              // d[c] of lane+1's first row
     int par = 0;                                  // step parity (NW > 1: buffer of the cross-warp handoff)
 
-    // Cross-warp handoff (NW > 1): writes into the parity buffer, ONE block barrier per step, reads after it.
-    // (Split arrive/sync named barriers were measured slower than the plain barrier: 6.1 vs 4.65 ms at
-    // 64x512 pairs of len 128.)
+    // (NW > 1: split arrive/sync named barriers were measured slower than the plain block barrier: 6.1 vs
+    // 4.65 ms at 64x512 pairs of len 128.)
     auto step = [&]() __attribute__((always_inline)) {
-        // next step's stencil column is c+1: the warp above needs this warp's first-row d[c+1] = dC as of NOW
-        // (made one step ago)
-        if (NW > 1 && lane == 0 && wid > 0) xdn[wid][par] = dC[0];
+        // next step's stencil column is c+1: lane-1 needs this lane's first-row d[c+1] = dC as of NOW (made
+        // one step ago), so this exchange does not wait for this step's production
+        dx[par][glane] = dC[0];
         // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
         // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
         double ca[RC], cb[RC];
@@ -176,7 +185,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 
         // ---- 2. the stencil: R rows x F fine columns in registers, anti-diagonal order ---------------
         double U[R][F];
-        double tnext[F];
 #pragma unroll
         for (int dgl = 0; dgl < R + F - 1; ++dgl) {
             double ss[F], tt[F];
@@ -204,10 +212,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 const int r = dgl - f;
                 if (r >= 0 && r < R) {
                     U[r][f] = fma(ca[r >> LOGD], ss[f], tt[f]);
-                    if (r == R - 1) {
-                        // hand the bottom-row value to lane+1 right away: it is consumed one step later
-                        tnext[f] = shfl_up1(U[r][f]);
-                        if (NW > 1 && lane == 31 && wid + 1 < NW) xtop[wid + 1 < NW ? wid + 1 : 0][par][f] = U[r][f];
+                    if (r == R - 1 && ((f & 1) || f == F - 1)) {
+                        // hand the bottom-row values to lane+1 as soon as a pair of them exists
+                        tx[par][f >> 1][glane + 1] = make_double2(U[r][f & ~1], U[r][f]);
                     }
                 }
             }
@@ -215,18 +222,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         topprev = tops[F - 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
-        // next step's stencil column is c+1: it needs lane+1's d[c+1] = lane+1's dC as of NOW (made one
-        // step ago), so this exchange does not wait for this step's production
-        dn = shfl_down1(dC[0]);
-        if (NW > 1) {
-            __syncthreads();
-            if (lane == 31 && wid + 1 < NW) dn = xdn[wid + 1 < NW ? wid + 1 : 0][par];
-        }
+        if (NW > 1) __syncthreads(); else __syncwarp();
+        dn = dx[par][glane + 1];
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-            double tb = 1.0;                      // grid row 0 is the boundary u = 1
-            if (NW > 1 && lane == 0 && wid > 0) tb = xtop[wid][par][f];
-            tops[f] = lane == 0 ? tb : tnext[f];
+        for (int h = 0; h < H; ++h) {
+            const double2 v = tx[par][h][glane];
+            tops[2 * h] = v.x;
+            if (2 * h + 1 < F) tops[2 * h + 1 < F ? 2 * h + 1 : 0] = v.y;
         }
         par ^= 1;
 
