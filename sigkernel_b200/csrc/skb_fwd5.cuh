@@ -25,6 +25,7 @@
 // Reference semantics replaced: sigkernel/cuda_backend.py:121-160 (+ :6-49), static_kernels.py:17-33,
 // 42-73, sigkernel.py:362-364, 607-613 -- see skb_solver.cuh for the mapping.
 #pragma once
+#include <type_traits>
 #include "skb_solver.cuh"
 
 namespace skb {
@@ -54,6 +55,27 @@ __device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ 
     return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB - 1)) * 4096, __double2loint(v));
 }
 
+// shared-memory accesses of the neighbour exchange: 32-bit shared addresses with compile-time offsets, so that
+// the per-step address arithmetic disappears (the buffer index is the position in the 3x unrolled loop)
+template <int OFF>
+__device__ __forceinline__ void sts_f64x2(unsigned base, double a, double b) {
+    asm volatile("st.shared.v2.f64 [%0 + %3], {%1, %2};" ::"r"(base), "d"(a), "d"(b), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void lds_f64x2(unsigned base, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2 + %3];" : "=d"(a), "=d"(b) : "r"(base), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64(unsigned base, double a) {
+    asm volatile("st.shared.f64 [%0 + %2], %1;" ::"r"(base), "d"(a), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64(unsigned base) {
+    double a;
+    asm volatile("ld.shared.f64 %0, [%1 + %2];" : "=d"(a) : "r"(base), "n"(OFF) : "memory");
+    return a;
+}
+
 // NW warps (32 NW lanes) share one pair: warp w+1 continues the wavefront of warp w (lane 0 of warp w+1 is
 // "lane 32 (w+1)"); the two values that cross the warp boundary every step (bottom row of lane 31 going down,
 // d of the next warp's first row going up) go through double-buffered shared memory and one block barrier.
@@ -74,14 +96,18 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 
     __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
     __shared__ int4 ring_s[RING];                // job stream: (job, x offset, y offset, -) in doubles
-    // Neighbour exchange through shared memory, double-buffered by step parity (one warp / block barrier per
-    // step separates the writes from the reads): lane g writes its bottom row to slot g+1 and reads the row
-    // above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0 needs no special case and a
-    // warp boundary (NW > 1) is just another slot; likewise the d value of the first node row goes UP one lane.
+    // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
+    // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
+    // slot g+1 and reads the row above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0
+    // needs no special case and a warp boundary (NW > 1) is just another slot; likewise the d value of the
+    // first node row goes UP one lane.
+    static_assert(UNR == 3, "the exchange buffers and the d history rotate with period 3");
     constexpr int H = (F + 1) / 2;
     constexpr int NL = 32 * NW;
-    __shared__ double2 tx[2][H][NL + 1];
-    __shared__ double dx[2][NL + 1];
+    constexpr int TXH = (NL + 1) * 16, TXQ = H * TXH;     // byte strides of tx[q][h][slot]
+    constexpr int DXQ = (NL + 1) * 8;                       // byte stride of dx[q][slot]
+    __shared__ double2 tx[3][H][NL + 1];
+    __shared__ double dx[3][NL + 1];
     if (KIND == KIND_RBF) {
         for (int j = glane; j < EXP_TAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
     }
@@ -92,17 +118,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // picks entry w up when ITS production column wraps for the w-th time, t steps later (lane 0 is at most
     // 32 NW - 1 steps, i.e. < RING/2 wraps, ahead of the last lane because N >= 4).  Until its first wrap
     // lane t > 0 works on a "virtual" pair (the data of the first real pair, all outputs suppressed).
-    volatile int4* const ring = ring_s;
-    const unsigned xstride = (unsigned)(M * Dp), ystride = (unsigned)(N * Dp);
+    const unsigned xstride = (unsigned)(M * Dp * 8), ystride = (unsigned)(N * Dp * 8);   // bytes (< 4 GB: host check)
     int job_next = 0;
-    unsigned xo, yo;                              // offsets (in doubles) of the production pair's paths
+    unsigned xo, yo;                              // byte offsets of the production pair's paths
     {
         int a, b;
         job_decode(p, p.job0 + first_job, a, b);
         xo = (unsigned)a * xstride;
         yo = (unsigned)b * ystride;
         if (glane == 0) {
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < 3; ++q) {
                 for (int h = 0; h < H; ++h) tx[q][h][0] = make_double2(1.0, 1.0);
                 dx[q][NL] = 0.0;
             }
@@ -121,25 +146,30 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // this lane holds grid row MM-1 (the output) in u[(orc + 1) * F - 1] iff 0 <= orc < RC
     const int orc = (M - 2) - glane * RC;
 
-    unsigned xoff[RC];
+    const char* xrow0[RC];                        // this lane's node rows in X_0 (clamped rows never reach a valid cell)
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) {
         int row = glane * RC + rc;
-        row = row < M ? row : M - 1;              // clamped rows never reach a valid cell
-        xoff[rc] = (unsigned)(row * Dp);
+        row = row < M ? row : M - 1;
+        xrow0[rc] = reinterpret_cast<const char*>(p.Xp) + (size_t)row * (Dp * 8);
     }
+    const unsigned txb = (unsigned)__cvta_generic_to_shared(&tx[0][0][glane]);   // read slot; write slot = +16
+    const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][glane]);      // write slot; read slot = +8
 
     double2 xr[XREG ? RC : 1][DP2];
-    const double* xb = p.Xp;
+    const double* xrow[XREG ? 1 : RC];            // !XREG: the rows are re-read every step
     const double* yp = p.Yp;                      // y row of the NEXT production column
     auto set_pair = [&]() {
-        xb = p.Xp + xo;
-        yp = p.Yp + yo;
-        if (XREG) {
+        yp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + yo);
 #pragma unroll
-            for (int rc = 0; rc < RC; ++rc)
+        for (int rc = 0; rc < RC; ++rc) {
+            const double* xp = reinterpret_cast<const double*>(xrow0[rc] + xo);
+            if (XREG) {
 #pragma unroll
-                for (int i = 0; i < DP2; ++i) xr[rc][i] = ldg2(xb + xoff[rc] + 2 * i);
+                for (int i = 0; i < DP2; ++i) xr[rc][i] = ldg2(xp + 2 * i);
+            } else {
+                xrow[XREG ? 0 : rc] = xp;
+            }
         }
     };
     set_pair();
@@ -165,14 +195,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) klast[rc] = dA[rc] = dB[rc] = dC[rc] = 0.0;
     double dn = 0.0;                              // d[c] of lane+1's first row
-    int par = 0;                                  // step parity (NW > 1: buffer of the cross-warp handoff)
 
     // (NW > 1: split arrive/sync named barriers were measured slower than the plain block barrier: 6.1 vs
     // 4.65 ms at 64x512 pairs of len 128.)
-    auto step = [&]() __attribute__((always_inline)) {
+    auto step = [&](auto qc) __attribute__((always_inline)) {
+        constexpr int Q = decltype(qc)::value;    // exchange buffer of this step
         // next step's stencil column is c+1: lane-1 needs this lane's first-row d[c+1] = dC as of NOW (made
         // one step ago), so this exchange does not wait for this step's production
-        dx[par][glane] = dC[0];
+        sts_f64<Q * DXQ>(dxb, dC[0]);
         // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
         // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
         double ca[RC], cb[RC];
@@ -214,7 +244,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     U[r][f] = fma(ca[r >> LOGD], ss[f], tt[f]);
                     if (r == R - 1 && ((f & 1) || f == F - 1)) {
                         // hand the bottom-row values to lane+1 as soon as a pair of them exists
-                        tx[par][f >> 1][glane + 1] = make_double2(U[r][f & ~1], U[r][f]);
+                        if (f == 0) sts_f64x2<Q * TXQ + 16>(txb, U[r][0], U[r][0]);
+                        if (f == 1) sts_f64x2<Q * TXQ + 16>(txb, U[r][0], U[r][1]);
+                        if (f == 2) sts_f64x2<Q * TXQ + TXH + 16>(txb, U[r][2], U[r][2]);
+                        if (f == 3) sts_f64x2<Q * TXQ + TXH + 16>(txb, U[r][2], U[r][3]);
+                        if (f == 4) sts_f64x2<Q * TXQ + 2 * TXH + 16>(txb, U[r][4], U[r][4]);
+                        if (f == 5) sts_f64x2<Q * TXQ + 2 * TXH + 16>(txb, U[r][4], U[r][5]);
+                        if (f == 6) sts_f64x2<Q * TXQ + 3 * TXH + 16>(txb, U[r][6], U[r][6]);
+                        if (f == 7) sts_f64x2<Q * TXQ + 3 * TXH + 16>(txb, U[r][6], U[r][7]);
                     }
                 }
             }
@@ -223,24 +260,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
         if (NW > 1) __syncthreads(); else __syncwarp();
-        dn = dx[par][glane + 1];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const double2 v = tx[par][h][glane];
-            tops[2 * h] = v.x;
-            if (2 * h + 1 < F) tops[2 * h + 1 < F ? 2 * h + 1 : 0] = v.y;
+        dn = lds_f64<Q * DXQ + 8>(dxb);
+        {
+            double vx, vy;
+            lds_f64x2<Q * TXQ>(txb, vx, vy);
+            tops[0] = vx;
+            if (F > 1) tops[F > 1 ? 1 : 0] = vy;
+            if (F > 2) { lds_f64x2<Q * TXQ + TXH>(txb, vx, vy); tops[F > 2 ? 2 : 0] = vx; tops[F > 3 ? 3 : 0] = vy; }
+            if (F > 4) {
+                lds_f64x2<Q * TXQ + 2 * TXH>(txb, vx, vy); tops[F > 4 ? 4 : 0] = vx; tops[F > 5 ? 5 : 0] = vy;
+                lds_f64x2<Q * TXQ + 3 * TXH>(txb, vx, vy); tops[F > 6 ? 6 : 0] = vx; tops[F > 7 ? 7 : 0] = vy;
+            }
         }
-        par ^= 1;
 
         // ---- 3. production: static kernel at node column e = c + LEAD (y row loaded one step ago) -----
         double dnew[RC];
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) {
-            double2 xv = XREG ? xr[XREG ? rc : 0][0] : ldg2(xb + xoff[rc]);
+            double2 xv = XREG ? xr[XREG ? rc : 0][0] : ldg2(xrow[XREG ? 0 : rc]);
             double acc = fma(xv.y, yq[0].y, xv.x + yq[0].x);
 #pragma unroll
             for (int i = 1; i < DP2; ++i) {
-                xv = XREG ? xr[XREG ? rc : 0][i] : ldg2(xb + xoff[rc] + 2 * i);
+                xv = XREG ? xr[XREG ? rc : 0][i] : ldg2(xrow[XREG ? 0 : rc] + 2 * i);
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
             if (KIND == KIND_RBF) acc = exp_neg5(acc, etab, p);
@@ -303,8 +344,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     ent.x = job;
                     ring_s[w & (RING - 1)] = ent;
                 } else if (w >= 0) {
-                    const volatile int4* e = ring + (w & (RING - 1));
-                    ent.x = e->x; ent.y = e->y; ent.z = e->z;
+                    ent = ring_s[w & (RING - 1)];     // written >= 1 step (= 1 barrier) ago
                 }
                 pjob = ent.x;
                 if (w >= 0 && ent.x < 0) done = true;
@@ -325,8 +365,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         } else {
             if (!__any_sync(FULL, alive)) break;
         }
-#pragma unroll
-        for (int it = 0; it < UNR; ++it) step();
+        step(std::integral_constant<int, 0>{});
+        step(std::integral_constant<int, 1>{});
+        step(std::integral_constant<int, 2>{});
     }
 }
 
