@@ -162,6 +162,23 @@ int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M,
                                           int scheme, int pairs, double* out, double* S,
                                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- kernel and its first / second directional derivative along gamma ----------------------
+ *
+ * Replaces k_kgrad's solve (sigkernel.py:504-593) and sigkernel_derivatives_Gram_cuda
+ * (cuda_backend.py:165-223) behind SigKernel.compute_kernel_and_derivatives_Gram (sigkernel.py:43-89).
+ * The caller evaluates the static kernel three times, exactly as the reference does (sigkernel.py:524-539):
+ *   K0 = Gram_matrix(X, Y), K1 = Gram_matrix(X + eps*gamma, Y), K2 = Gram_matrix(X + 2*eps*gamma, Y),
+ * each (A,B,M,N) device fp64, and passes the COARSE matrices; the finite differences in eps, the second
+ * differences, the dyadic refinement and the three coupled stencils run on the device.
+ *   out3 (A*B, 3): k, k_gamma, k_gamma_gamma at the end point, interleaved per pair.
+ * workspace: skb_deriv_workspace_bytes(A, B, M, N).  Limit: 9 * (MM + 1) doubles of shared memory per pair
+ * (MM = (M-1) << dyadic_order <= 2843).
+ */
+size_t skb_deriv_workspace_bytes(int A, int B, int M, int N);
+int skb_sigkernel_derivatives_from_static(const double* K0, const double* K1, const double* K2,
+                                          int A, int B, int M, int N, int dyadic_order, double eps,
+                                          double* out3, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

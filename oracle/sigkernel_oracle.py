@@ -52,8 +52,9 @@ def _c():
                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
         lib.skb_oracle_solve_gram_corner.argtypes = [dp, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                                      ctypes.c_int, dp, dp]
+        lib.skb_oracle_solve_derivatives.argtypes = [dp, dp, dp, ctypes.c_long, ctypes.c_int, ctypes.c_int, dp, dp]
         for f in (lib.skb_oracle_solve_batch, lib.skb_oracle_solve_gram,
-                  lib.skb_oracle_solve_gram_corner):
+                  lib.skb_oracle_solve_gram_corner, lib.skb_oracle_solve_derivatives):
             f.restype = None
         _clib = lib
     return _clib
@@ -392,3 +393,38 @@ def batch_grad_points_analytic(X, Y, static_kernel, dyadic_order, naive=False, b
     kind = "rbf" if isinstance(static_kernel, RBFKernel) else "linear_batch"
     dk = _d1k(static_kernel, kind, X[:, :, None, :], Y[:, None, :, :], Ks)
     return U[:, -1, -1], grad_points_from_S(S, dk), S
+
+
+# ---------------------------------------------------------------------------------------
+# kernel + first / second directional derivative along gamma
+# (sigkernel.py:504-593 k_kgrad; solver = cuda_backend.py:165-223, see solver.c)
+# ---------------------------------------------------------------------------------------
+def derivative_increments(X, Y, gamma, static_kernel, dyadic_order, eps=1e-4):
+    """The three refined increment tensors of k_kgrad (sigkernel.py:524-544), operation by operation."""
+    G = static_kernel.Gram_matrix(X, Y)
+    inc = second_difference(G)
+    d1 = -(1. / eps) * G
+    d2 = (1. / eps) * static_kernel.Gram_matrix(X + eps * gamma, Y)
+    inc_d = second_difference(d1) + second_difference(d2)
+    dd1 = -(1. / eps) * d1
+    dd2 = -(2. / eps) * d2
+    dd3 = (1. / eps ** 2) * static_kernel.Gram_matrix(X + 2. * eps * gamma, Y)
+    inc_dd = second_difference(dd1) + second_difference(dd2) + second_difference(dd3)
+    return refine(inc, dyadic_order), refine(inc_d, dyadic_order), refine(inc_dd, dyadic_order)
+
+
+def solve_derivatives(inc, inc_d, inc_dd):
+    """(A,B,MM,NN) x 3 -> K, K_diff, K_diffdiff, each (A,B)."""
+    A, B, MM, NN = inc.shape
+    arrs = [np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float64) for t in (inc, inc_d, inc_dd)]
+    out = np.empty((A * B, 3), dtype=np.float64)
+    work = np.empty(3 * (MM + 1) * (NN + 1), dtype=np.float64)
+    _c().skb_oracle_solve_derivatives(_dptr(arrs[0]), _dptr(arrs[1]), _dptr(arrs[2]), A * B, MM, NN,
+                                      _dptr(out), _dptr(work))
+    out = torch.from_numpy(out).reshape(A, B, 3)
+    return out[..., 0].clone(), out[..., 1].clone(), out[..., 2].clone()
+
+
+def compute_kernel_and_derivatives_Gram(X, Y, gamma, static_kernel, dyadic_order, eps=1e-4):
+    """SigKernel.compute_kernel_and_derivatives_Gram (sigkernel.py:43-89) without the max_batch splitting."""
+    return solve_derivatives(*derivative_increments(X, Y, gamma, static_kernel, dyadic_order, eps))

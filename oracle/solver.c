@@ -135,3 +135,50 @@ void skb_oracle_solve_gram_corner(const double *inc, long pairs, int MM, int NN,
         out[p] = up[NN];
     }
 }
+
+/* sigkernel/cuda_backend.py:165-223  sigkernel_derivatives_Gram_cuda -> skb_oracle_solve_derivatives
+ * (the reference's CPU branch of k_kgrad is broken, sigkernel.py:588 vs cython_backend.pyx:176, so the
+ * restatement follows the Numba kernel; pinned against that kernel run under Numba's CUDA simulator,
+ * tests/golden/make_golden.py).  Row-major sweep instead of the kernel's anti-diagonal order: every cell
+ * reads only finished cells, the arithmetic per cell is the kernel's, statement by statement.
+ * inc, incd, incdd: (pairs, MM, NN); out: (pairs, 3) = K, K_diff, K_diffdiff at node (MM, NN);
+ * work: 3 * (MM+1) * (NN+1) doubles. */
+void skb_oracle_solve_derivatives(const double *inc, const double *incd, const double *incdd, long pairs,
+                                  int MM, int NN, double *out, double *work)
+{
+    const size_t ld = (size_t)NN + 1, nodes = (size_t)(MM + 1) * ld, cells = (size_t)MM * NN;
+    double *K = work, *Kd = work + nodes, *Kdd = work + 2 * nodes;
+    for (long p = 0; p < pairs; ++p) {
+        const double *g = inc + p * cells, *gd = incd + p * cells, *gdd = incdd + p * cells;
+        for (size_t k = 0; k < nodes; ++k) { K[k] = 0.; Kd[k] = 0.; Kdd[k] = 0.; }
+        for (int j = 0; j <= NN; ++j) K[j] = 1.;
+        for (int i = 0; i <= MM; ++i) K[(size_t)i * ld] = 1.;
+        for (int i = 1; i <= MM; ++i) {
+            for (int j = 1; j <= NN; ++j) {
+                const double in = g[(size_t)(i - 1) * NN + j - 1];
+                const double ind = gd[(size_t)(i - 1) * NN + j - 1];
+                const double indd = gdd[(size_t)(i - 1) * NN + j - 1];
+                const size_t c11 = (size_t)i * ld + j, c01 = c11 - ld, c10 = c11 - 1, c00 = c01 - 1;
+                const double k01 = K[c01], k10 = K[c10], k00 = K[c00];
+                const double k01d = Kd[c01], k10d = Kd[c10], k00d = Kd[c00];
+                const double k01dd = Kdd[c01], k10dd = Kdd[c10], k00dd = Kdd[c00];
+                const double k11 = (k01 + k10) * (1. + 0.5 * in + (1. / 12) * (in * in)) - k00 * (1. - (1. / 12) * (in * in));
+                K[c11] = k11;
+                const double f1 = k00 * ind + k00d * in;
+                const double f2 = k01 * ind + k01d * in;
+                const double f3 = k10 * ind + k10d * in;
+                const double f4 = k11 * ind + (k01d + k10d - k00d + f1) * in;
+                const double k11d = k01d + k10d - k00d + 0.25 * (f1 + f2 + f3 + f4);
+                Kd[c11] = k11d;
+                const double g1 = k00 * indd + 2. * k00d * ind + k00dd * in;
+                const double g2 = k01 * indd + 2. * k01d * ind + k01dd * in;
+                const double g3 = k10 * indd + 2. * k10d * ind + k10dd * in;
+                const double g4 = k11 * indd + 2. * k11d * ind + (k01dd + k10dd - k00dd + g1) * in;
+                Kdd[c11] = k01dd + k10dd - k00dd + 0.25 * (g1 + g2 + g3 + g4);
+            }
+        }
+        out[3 * p + 0] = K[nodes - 1];
+        out[3 * p + 1] = Kd[nodes - 1];
+        out[3 * p + 2] = Kdd[nodes - 1];
+    }
+}

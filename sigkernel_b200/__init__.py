@@ -10,7 +10,7 @@ from ._lib import SigKernelB200Error                 # noqa: F401
 from .static_kernels import (LinearKernel, RBFKernel, RBF_CEXP_Kernel, RBF_SQR_Kernel,  # noqa: F401
                              Linear_ID_Kernel, RBF_ID_Kernel, CEXP, cos_exp_kernel)
 from .sigkernel import (SigKernel, _SigKernel, _SigKernelGram, hypothesis_test, SigCHSIC,  # noqa: F401
-                        c_alpha)
+                        c_alpha, k_kgrad)
 from . import ops                                    # noqa: F401
 from . import distributed                            # noqa: F401
 

@@ -34,6 +34,8 @@ SYMBOLS = {
     "skb_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "skb_sigkernel_sensitivity_from_static": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "skb_deriv_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "skb_sigkernel_derivatives_from_static": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
 }
 
 

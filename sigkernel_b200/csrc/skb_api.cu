@@ -370,4 +370,19 @@ int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M,
                        workspace_bytes - kCounterBytes, (cudaStream_t)stream);
 }
 
+size_t skb_deriv_workspace_bytes(int A, int B, int M, int N) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2) return 0;
+    return align256((size_t)A * B * (M - 1) * (N - 1) * 3 * sizeof(double)) + 256;
+}
+
+int skb_sigkernel_derivatives_from_static(const double* K0, const double* K1, const double* K2, int A, int B, int M,
+                                          int N, int dyadic_order, double eps, double* out3, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || dyadic_order < 0 || dyadic_order > 20 || !(eps > 0.0)) return SKB_ERR_BAD_SHAPE;
+    if (!K0 || !K1 || !K2 || !out3) return SKB_ERR_NULL;
+    if (!workspace || workspace_bytes < skb_deriv_workspace_bytes(A, B, M, N)) return SKB_ERR_WORKSPACE;
+    double* inc3 = (double*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    return launch_derivatives(K0, K1, K2, (long)A * B, M, N, dyadic_order, eps, inc3, out3, (cudaStream_t)stream);
+}
+
 }  // extern "C"

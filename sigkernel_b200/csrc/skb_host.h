@@ -61,6 +61,11 @@ int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double
 // padded row width the fused kinds are specialised for
 int padded_dim(int D);
 
+// kernel + directional derivatives (skb_deriv.cu): K0, K1, K2 coarse static matrices (pairs, M, N);
+// inc3 scratch (pairs, M-1, N-1, 3); out3 (pairs, 3)
+int launch_derivatives(const double* K0, const double* K1, const double* K2, long pairs, int M, int N, int d,
+                       double eps, double* inc3, double* out3, cudaStream_t st);
+
 // per-group launchers (one translation unit each, to parallelise compilation)
 typedef int (*group_fn)(int mode, int kind, int rc, int logd, int dp2, bool exact, const KArgs&, cudaStream_t);
 int launch_group_fwd_rbf(int, int, int, int, int, bool, const KArgs&, cudaStream_t);

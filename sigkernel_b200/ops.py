@@ -135,3 +135,22 @@ def sensitivity_from_static(Ks, dyadic_order, pairs="gram", naive=False):
     if pairs == "batch":
         return out, S
     return out.view(A, B), S.view(A, B, M - 1, N - 1)
+
+
+def kernel_and_derivatives_from_static(K0, K1, K2, dyadic_order, eps):
+    """K0, K1, K2 (A,B,M,N): Gram_matrix(X, Y), Gram_matrix(X + eps*gamma, Y), Gram_matrix(X + 2*eps*gamma, Y)
+    -> (k, k_gamma, k_gamma_gamma), each (A,B) fp64 (reference k_kgrad, sigkernel.py:504-593)."""
+    if not (K0.is_cuda and K1.is_cuda and K2.is_cuda):
+        raise _lib.SigKernelB200Error("sigkernel_b200 runs on CUDA tensors only (no CPU fallback)")
+    if not (K0.shape == K1.shape == K2.shape) or K0.dim() != 4:
+        raise _lib.SigKernelB200Error(f"expected three (A,B,M,N) static matrices, got {tuple(K0.shape)}, {tuple(K1.shape)}, {tuple(K2.shape)}")
+    Ks = [k.detach().to(torch.float64).contiguous() for k in (K0, K1, K2)]
+    A, B, M, N = Ks[0].shape
+    with torch.cuda.device(Ks[0].device):
+        out = torch.empty((A * B, 3), dtype=torch.float64, device=Ks[0].device)
+        ws, nbytes = _workspace(lib.skb_deriv_workspace_bytes(A, B, M, N), Ks[0].device)
+        check(lib.skb_sigkernel_derivatives_from_static(Ks[0].data_ptr(), Ks[1].data_ptr(), Ks[2].data_ptr(), A, B, M, N,
+                                                        int(dyadic_order), float(eps), out.data_ptr(), ws.data_ptr(),
+                                                        nbytes, _stream()))
+    out = out.view(A, B, 3)
+    return out[..., 0].contiguous(), out[..., 1].contiguous(), out[..., 2].contiguous()

@@ -162,6 +162,13 @@ class SigKernel:
         X, Y = _prepare(self.static_kernel, X, Y, gram=True)
         return _SigKernelGram.apply(X, Y, self.static_kernel, self.dyadic_order, sym, self._naive_solver)
 
+    def compute_kernel_and_derivatives_Gram(self, X, Y, gamma, max_batch=100):
+        """X (batch_x, len_x, dim), Y (batch_y, len_y, dim), gamma (batch_x, len_x, dim) ->
+        k(X^i, Y^j), its directional derivative along gamma^i and the second one, each (batch_x, batch_y)
+        (reference sigkernel.py:43-89 / k_kgrad :504-593).  No gradients flow through this call, as in the
+        reference (every tensor is detached there before the solve)."""
+        return k_kgrad(X, Y, gamma, self.dyadic_order, self.static_kernel)
+
     def compute_distance(self, X, Y, max_batch=100):
         """mean_a ||S(X^a) - S(Y^a)||^2."""
         assert not Y.requires_grad, "the second input should not require grad"
@@ -191,6 +198,19 @@ class SigKernel:
         K_YY = self.compute_Gram(Y, Y, sym=True, max_batch=max_batch)
         K_XY = self.compute_Gram(X, Y, sym=False, max_batch=max_batch)
         return _offdiag_mean(K_XX) + _offdiag_mean(K_YY) - 2. * torch.mean(K_XY)
+
+
+def k_kgrad(X, Y, gamma, dyadic_order, static_kernel, eps=1e-4):
+    """Signature kernel and its first / second directional derivatives along gamma (reference
+    sigkernel.py:504-593).  The static kernel is evaluated three times through the plugin interface, as the
+    reference does (:524-539); the finite differences in eps, the second differences, the dyadic refinement
+    and the three coupled PDE stencils (cuda_backend.py:165-223) run in one CUDA kernel pair."""
+    with torch.no_grad():
+        K0 = static_kernel.Gram_matrix(X, Y)
+        K1 = static_kernel.Gram_matrix(X + eps * gamma, Y)
+        K2 = static_kernel.Gram_matrix(X + 2. * eps * gamma, Y)
+        K, Kd, Kdd = ops.kernel_and_derivatives_from_static(K0, K1, K2, dyadic_order, eps)
+    return K.to(X.dtype), Kd.to(X.dtype), Kdd.to(X.dtype)
 
 
 def c_alpha(m, alpha):

@@ -137,8 +137,74 @@ def run_case(case):
     return meta
 
 
+# Directional derivatives (sigkernel.py:43-89, 504-593).  The reference's CPU branch of k_kgrad is broken
+# (sigkernel.py:588 unpacks three arrays from a function returning one, cython_backend.pyx:176) and its GPU
+# branch needs Numba-CUDA on a device, so these fixtures run the reference's OWN kernel
+# `sigkernel_derivatives_Gram_cuda` (cuda_backend.py:165-223) under Numba's CUDA simulator, fed by the
+# reference's own static kernels and `tile`, with k_kgrad's increment build (sigkernel.py:524-544) applied
+# line by line.  M_inc is zero-padded by one row / column: the reference launches len+1 threads that read
+# one element out of bounds.  Run with NUMBA_ENABLE_CUDASIM=1:
+#     NUMBA_ENABLE_CUDASIM=1 python tests/golden/make_golden.py deriv
+DERIV_CASES = [
+    ("deriv_rbf_d1", ("rbf", 0.5), 1, "rand", 30, (2, 5, 2), (3, 4, 2)),
+    ("deriv_rbf_d0", ("rbf", 1.0), 0, "randn", 31, (3, 6, 3), (2, 7, 3)),
+    ("deriv_linear_d2", ("linear", 1.0), 2, "bm", 32, (2, 4, 2), (2, 5, 2)),
+]
+
+
+def run_deriv_case(case):
+    from sigkernel.cuda_backend import sigkernel_derivatives_Gram_cuda
+    from sigkernel.sigkernel import tile
+    name, kspec, d, kind, seed, sx, sy = case
+    X, Y = gen(kind, seed, sx, sy)
+    g = torch.Generator().manual_seed(seed + 1000)
+    gamma = torch.rand(sx, dtype=torch.float64, generator=g)
+    sk = make_kernel(kspec)
+    eps = 1e-4
+    A, M, _ = sx
+    B, N, _ = sy
+    MM, NN = (2 ** d) * (M - 1), (2 ** d) * (N - 1)
+
+    def d2(G):
+        return G[:, :, 1:, 1:] + G[:, :, :-1, :-1] - G[:, :, 1:, :-1] - G[:, :, :-1, 1:]
+
+    G = sk.Gram_matrix(X, Y)
+    G_ = d2(G)
+    Gd1 = -(1. / eps) * G
+    Gd2 = (1. / eps) * sk.Gram_matrix(X + eps * gamma, Y)
+    Gd_ = d2(Gd1) + d2(Gd2)
+    Gdd1 = -(1. / eps) * Gd1
+    Gdd2 = -(2. / eps) * Gd2
+    Gdd3 = (1. / eps ** 2) * sk.Gram_matrix(X + 2. * eps * gamma, Y)
+    Gdd_ = d2(Gdd1) + d2(Gdd2) + d2(Gdd3)
+
+    def refine(T):
+        return tile(tile(T, 2, 2 ** d) / float(2 ** d), 3, 2 ** d) / float(2 ** d)
+
+    def pad(T):
+        return np.pad(T.numpy(), ((0, 0), (0, 0), (0, 1), (0, 1)))
+
+    K = np.zeros((A, B, MM + 2, NN + 2))
+    Kd, Kdd = np.zeros_like(K), np.zeros_like(K)
+    K[:, :, 0, :] = 1.
+    K[:, :, :, 0] = 1.
+    tpb = max(MM + 1, NN + 1)
+    sigkernel_derivatives_Gram_cuda[(A, B), tpb](pad(refine(G_)), pad(refine(Gd_)), pad(refine(Gdd_)),
+                                                 MM + 1, NN + 1, 2 * tpb - 1, K, Kd, Kdd)
+    meta = dict(name=name, op="deriv", static=kspec[0], param=kspec[1], dyadic_order=d, data=kind, seed=seed, eps=eps)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X.numpy(), Y=Y.numpy(), gamma=gamma.numpy(),
+                        meta=json.dumps(meta), K=K[:, :, MM, NN], K_diff=Kd[:, :, MM, NN], K_diffdiff=Kdd[:, :, MM, NN])
+    return meta
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "deriv":
+        assert os.environ.get("NUMBA_ENABLE_CUDASIM") == "1", "set NUMBA_ENABLE_CUDASIM=1"
+        for c in DERIV_CASES:
+            m = run_deriv_case(c)
+            print("wrote", m["name"], m["op"])
+        sys.exit(0)
     for c in CASES:
         m = run_case(c)
         print("wrote", m["name"], m["op"])
