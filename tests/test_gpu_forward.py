@@ -282,3 +282,60 @@ def test_generic_exact_bitwise(skb, O):
     Ks = O.RBFKernel(0.5).Gram_matrix(X, Y)
     ref = torch.from_numpy(O.solve_gram(O.increments(Ks, 1).numpy()))[:, :, -1, -1]
     assert torch.equal(skb.ops.sigkernel_forward_from_static(Ks.cuda(), 1, "gram", exact=True).cpu(), ref)
+
+
+# ---- fwd5_kernel (skb_fwd5.cuh): job ring, virtual start, 1 / 2 / 4 warps per pair ---------------------
+FWD5_SHAPES = [
+    # A, B, M, N, D, d    what it stresses
+    (37, 41, 9, 4, 2, 1),      # N = 4: production a whole pair ahead, a ring entry every 4 steps, lanes >= N start virtual several times
+    (23, 19, 12, 5, 3, 2),     # N = 5, wrap column 0
+    (3, 2, 64, 64, 5, 2),      # the headline strip (RC=2, d=2, Dp=6)
+    (5, 4, 33, 6, 9, 0),       # Dp = 10, RC = 2, d = 0
+    (3, 3, 100, 11, 8, 1),     # RC = 4 at one warp would be 8 rows: 2 warps per pair (RC = 2)
+    (2, 3, 128, 128, 8, 2),    # cfg5's strip: 2 warps per pair
+    (2, 2, 250, 9, 3, 2),      # 4 warps per pair (RC = 2)
+    (2, 2, 70, 7, 1, 3),       # d = 3: RC = 1 with 4 warps per pair
+    (6, 6, 31, 31, 4, 3),      # RC = 1, d = 3, one warp
+]
+
+
+@pytest.mark.parametrize("A,B,M,N,D,d", FWD5_SHAPES)
+@pytest.mark.parametrize("static", ["rbf", "linear"])
+def test_fwd5_shapes_vs_oracle(skb, O, A, B, M, N, D, d, static):
+    X = make_paths("bm", 700 + M, (A, M, D))
+    Y = make_paths("bm", 800 + N, (B, N, D))
+    ok = O.RBFKernel(0.8) if static == "rbf" else O.LinearKernel()
+    sk = skb.SigKernel(skb.RBFKernel(0.8) if static == "rbf" else skb.LinearKernel(), d)
+    for wpsm in (0, 4):        # default residency, and few resident warps so that every stream runs many pairs
+        skb._lib.lib.skb_set_warps_per_sm(wpsm)
+        try:
+            got = sk.compute_Gram(X.cuda(), Y.cuda())
+        finally:
+            skb._lib.lib.skb_set_warps_per_sm(0)
+        assert fwd_err(got.cpu().numpy(), O.compute_Gram(X, Y, ok, d).numpy()) <= FWD_TOL
+    if A == B:
+        assert fwd_err(sk.compute_kernel(X.cuda(), Y.cuda()).cpu().numpy(), O.compute_kernel(X, Y, ok, d).numpy()) <= FWD_TOL
+        if M == N:
+            Gs = sk.compute_Gram(X.cuda(), X.cuda(), sym=True)
+            assert torch.equal(Gs, Gs.T)
+            assert fwd_err(Gs.cpu().numpy(), O.compute_Gram(X, X, ok, d).numpy()) <= FWD_TOL
+
+
+def test_fwd5_long_stream_single_block(skb, O):
+    """One resident block streams 1500 pairs of 4-point paths: exercises the ring far beyond its depth."""
+    X, Y = make_paths("rand", 91, (30, 5, 2)), make_paths("rand", 92, (50, 4, 2))
+    ref = O.compute_Gram(X, Y, O.RBFKernel(0.5), 2)
+    import ctypes
+    lib = skb._lib.lib
+    Xc, Yc = X.cuda(), Y.cuda()
+    out = torch.empty(30 * 50, dtype=torch.float64, device="cuda")
+    nbytes = lib.skb_fwd_workspace_bytes(30, 50, 5, 4, 2, 2, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    # warps_per_sm = 1 still gives 148 blocks; 1500 pairs / 148 blocks ~ 10 pairs per stream
+    lib.skb_set_warps_per_sm(1)
+    try:
+        skb._lib.check(lib.skb_sigkernel_fwd(Xc.data_ptr(), Yc.data_ptr(), 0, 30, 50, 5, 4, 2, 2, 1, ctypes.c_double(0.5), 0, 0, 0,
+                                             out.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+    finally:
+        lib.skb_set_warps_per_sm(0)
+    assert fwd_err(out.view(30, 50).cpu().numpy(), ref.numpy()) <= FWD_TOL
