@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             for (int f = 0; f < F; ++f) {
                 const int r = dgl - f;
                 if (r >= 0 && r < R) {
+                    // (measured: a DFMA with three distinct register operands costs one issue cycle more
+                    //  than a two-operand DP instruction; DMUL + DADD instead of it is slower still)
                     U[r][f] = fma(ca[r >> LOGD], ss[f], tt[f]);
                     if (r == R - 1 && ((f & 1) || f == F - 1)) {
                         // hand the bottom-row values to lane+1 as soon as a pair of them exists
