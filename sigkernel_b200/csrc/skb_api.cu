@@ -229,7 +229,9 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
-    const bool use5 = fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1);
+    const bool use5 = fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
+                      (size_t)A * M * padded_dim(D) * sizeof(double) < ((size_t)1 << 32) &&
+                      (size_t)B * N * padded_dim(D) * sizeof(double) < ((size_t)1 << 32);   // 32-bit byte offsets in the job ring
     if (use5 && kind == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on that path
     rc = launch_prep(X, io_dtype, Xp, nullptr, A, M, D, Dp, cx, nsc, st);
     if (rc) return rc;
@@ -290,7 +292,7 @@ int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, in
 // shared driver of the two backward entry points: forward-with-store then reversed sweep, in chunks
 // of pairs whose forward grids fit the scratch part of the workspace
 static int run_adjoint(int kind, int rev_mode, KArgs fa, KArgs ra, int d, long njobs, double* scratch_base,
-                       size_t scratch_bytes, cudaStream_t st) {
+                       size_t scratch_bytes, cudaStream_t st, bool v5 = false) {
     const size_t per = grid_doubles_per_pair(fa.M, fa.N, d) * sizeof(double);
     const size_t pad = front_pad_doubles(fa.M, d) * sizeof(double);
     if (per == 0) return SKB_ERR_UNSUPPORTED;
@@ -303,9 +305,9 @@ static int run_adjoint(int kind, int rev_mode, KArgs fa, KArgs ra, int d, long n
         fa.job0 = ra.job0 = j0;
         fa.njobs = ra.njobs = nj;
         fa.scratch = ra.scratch = grid;
-        int rc = launch_solver(MODE_FWD_STORE, kind, d, false, fa, st);
+        int rc = v5 ? launch_adjoint5(MODE_FWD_STORE, kind, d, fa, st) : launch_solver(MODE_FWD_STORE, kind, d, false, fa, st);
         if (rc) return rc;
-        rc = launch_solver(rev_mode, kind, d, false, ra, st);
+        rc = v5 ? launch_adjoint5(rev_mode, kind, d, ra, st) : launch_solver(rev_mode, kind, d, false, ra, st);
         if (rc) return rc;
     }
     return SKB_OK;
@@ -336,6 +338,10 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     double* Yr = (double*)(w + kCounterBytes + 2 * xb + yb);
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
+    const int kind5 = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    const bool v5 = adjoint5_applies(kind5, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
+                    (size_t)A * M * Dp * sizeof(double) < ((size_t)1 << 32) && (size_t)B * N * Dp * sizeof(double) < ((size_t)1 << 32);
+    if (v5 && kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on the v5 path
     rc = launch_prep(X, io_dtype, Xp, Xr, A, M, D, Dp, cx, nsc, st);
     if (rc) return rc;
     rc = launch_prep(Y, io_dtype, Yp, Yr, B, N, D, Dp, 1.0, nsc, st);
@@ -348,8 +354,7 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     KArgs ra = fa;
     ra.Xp = Xr; ra.Yp = Yr; ra.out = nullptr; ra.grad = grad_points;
     ra.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
-    return run_adjoint(static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, MODE_REV_GRAD, fa, ra, dyadic_order,
-                       nj, (double*)(w + fixed), workspace_bytes - fixed, st);
+    return run_adjoint(kind5, MODE_REV_GRAD, fa, ra, dyadic_order, nj, (double*)(w + fixed), workspace_bytes - fixed, st, v5);
 }
 
 int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,

@@ -180,17 +180,52 @@ bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     return fwd5_plan(M, logd, nullptr) > 0;
 }
 
-int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
-    int rcp = 0;
-    const int nw = fwd5_plan(args.M, logd, &rcp);
-    if (nw == 0) return SKB_ERR_UNSUPPORTED;
+static void fill_v5_constants(KArgs& args, int logd) {
     args.kscale = fwd5_kscale(logd);
+    args.inv_kscale = 1.0 / args.kscale;
     args.sqrt3 = sqrt(3.0);
     args.ek = 369.32993046757463;                 // 256 / ln 2
     args.ehi = -0x1.62e42fee00000p-9;             // ln2/256 = hi + lo; hi has 21 trailing zero bits
     args.elo = -0x1.a39ef35793c76p-41;
     args.e4 = 1.0 / 24.0;
     args.e3 = 1.0 / 6.0;
+}
+
+// SKB_ADJ5_SHAPES of skb_fwd5.cuh: one warp per pair, dyadic order >= 1, <= 8 fine rows per lane
+static bool adjoint5_shape_ok(int rc, int logd) { return (rc == 1 && logd >= 1 && logd <= 3) || (rc == 2 && logd >= 1 && logd <= 2); }
+
+bool adjoint5_applies(int kind, int M, int N, int D, int logd, bool s1) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("SKB_ADJ5");       // development switch: SKB_ADJ5=0 forces the v4 adjoint kernels
+        on = e ? atoi(e) : 1;
+    }
+    if (!on || s1 || N < 4) return false;
+    if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
+    const int Dp = padded_dim(D);
+    if (Dp != 4 && Dp != 6 && Dp != 10) return false;
+    if (solver_rows_per_lane(M, logd) < 0) return false;
+    return adjoint5_shape_ok(coarse_rows_per_lane(M), logd);
+}
+
+int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
+    const int rcp = coarse_rows_per_lane(args.M);
+    fill_v5_constants(args, logd);
+    args.pitch = 32L * (rcp << logd);
+    if (!args.counter) return SKB_ERR_WORKSPACE;
+    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    if (rc) return rc;
+    const bool rbf = kind == KIND_RBF;
+    if (mode == 1) return rbf ? launch_group_adj5_rbf_store(rcp, logd, args.Dp / 2, args, st) : launch_group_adj5_lin_store(rcp, logd, args.Dp / 2, args, st);
+    if (mode == 3) return rbf ? launch_group_adj5_rbf_rev(rcp, logd, args.Dp / 2, args, st) : launch_group_adj5_lin_rev(rcp, logd, args.Dp / 2, args, st);
+    return SKB_ERR_UNSUPPORTED;
+}
+
+int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
+    int rcp = 0;
+    const int nw = fwd5_plan(args.M, logd, &rcp);
+    if (nw == 0) return SKB_ERR_UNSUPPORTED;
+    fill_v5_constants(args, logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;

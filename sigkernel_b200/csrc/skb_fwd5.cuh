@@ -34,6 +34,10 @@ namespace skb {
 // warps per SM); larger strips stay with solver_kernel.  Keep in sync with fwd5_shape_ok() (skb_dispatch.cu).
 #define SKB_FWD5_SHAPES(X) X(1, 0) X(1, 1) X(1, 2) X(1, 3) X(2, 0) X(2, 1) X(2, 2) X(4, 0)
 
+// shapes of the adjoint modes: one warp per pair, dyadic order >= 1 (MM and the strips even: 16-byte grid rows).
+// Keep in sync with adjoint5_shape_ok() (skb_dispatch.cu).
+#define SKB_ADJ5_SHAPES(X) X(1, 1) X(1, 2) X(1, 3) X(2, 1) X(2, 2)
+
 // exp(x) for x <= ~0, table-driven as exp_neg(); the underflow guard clamps x to >= -700.x through an
 // unsigned min on the high word (negative doubles order like their unsigned high words); NaN (canonical,
 // sign clear) passes through.
@@ -79,10 +83,22 @@ __device__ __forceinline__ double lds_f64(unsigned base) {
 // NW warps (32 NW lanes) share one pair: warp w+1 continues the wavefront of warp w (lane 0 of warp w+1 is
 // "lane 32 (w+1)"); the two values that cross the warp boundary every step (bottom row of lane 31 going down,
 // d of the next warp's first row going up) go through double-buffered shared memory and one block barrier.
-template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR>
+//
+// MODE 0            forward only: out[pair] = u[MM, NN]
+// MODE_FWD_STORE    additionally stores u[p, q] (the diagonal input of every cell) for the adjoint pass, same
+//                   scratch layout as solver_kernel: [job][fine column q][32 R row pitch]
+// MODE_REV_GRAD     the same sweep on the REVERSED paths (the reference's flipped-increment solve,
+//                   sigkernel.py:438-469), multiplied cell by cell with the stored forward grid (read one step
+//                   ahead), reduced to coarse sensitivities S and contracted with the analytic static-kernel
+//                   derivative into per-point gradients (sigkernel.py:470-500), see solver_kernel
+template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0>
 __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int F = 1 << LOGD;
     constexpr int R = RC * F;
+    constexpr bool STORE = MODE == MODE_FWD_STORE, REVG = MODE == MODE_REV_GRAD;
+    static_assert(MODE == 0 || STORE || REVG, "unknown mode");
+    static_assert(MODE == 0 || (NW == 1 && LOGD >= 1), "the adjoint modes use one warp per pair and 16-byte grid rows");
+    constexpr bool PREF = REVG && (F * R <= 8);  // stored grid read one step ahead into registers
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
@@ -182,6 +198,45 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
     for (int i = 0; i < DP2; ++i) yq[i] = ldg2(yp + 2 * i);
 
+    // ---- adjoint modes -------------------------------------------------------------------------------
+    extern __shared__ double gacc[];              // REV_GRAD: accumulators [(rc * (D + 1) + k) * 32 + lane]
+    const int D = p.D;
+    const long NNf = (long)(N - 1) << LOGD, MMl = (long)(M - 1) << LOGD;
+    unsigned sxo = xo, syo = yo;                  // REV_GRAD: byte offsets of the STENCIL stream's paths
+    const double* syp = p.Yp;                     // REV_GRAD: y row of the stencil column
+    double Sprev[RC], Slast_cur = 0.0, Slast_prev = 0.0;
+#pragma unroll
+    for (int rc = 0; rc < RC; ++rc) Sprev[rc] = 0.0;
+    double fw[REVG ? F : 1][REVG ? R : 1];        // forward values of the cells of this step (reversed row order)
+    if (REVG) {
+        for (int i = 0; i < RC * (D + 1); ++i) gacc[i * 32 + lane] = 0.0;
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+#pragma unroll
+            for (int r = 0; r < R; ++r) fw[REVG ? f : 0][REVG ? r : 0] = 0.0;
+    }
+    // rows of the stored grid this lane reads for (job, column): reversed coordinates, each lane's R values of
+    // one fine column are contiguous (the lanes of a warp are at 32 different columns, so a sector is written
+    // and read by ONE lane within one step; a layout that spreads a lane's rows over the row to "coalesce" the
+    // warp was measured 2.3x slower: partial lines get evicted and read back)
+    auto load_fw = [&](int job_, int col_) {
+        if (REVG) {
+            const bool real = job_ >= 0 && col_ < N - 1;
+            const double* srow = p.scratch + (((long)(real ? job_ : 0) * NNf + (NNf - 1 - (long)(real ? col_ : 0) * F)) * p.pitch +
+                                              (MMl - (long)(lane + 1) * R));
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int r2 = 0; r2 < R / 2; ++r2) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (real) v = *reinterpret_cast<const double2*>(srow - (long)f * p.pitch + 2 * r2);
+                    fw[REVG ? f : 0][REVG ? R - 1 - 2 * r2 : 0] = v.x;
+                    fw[REVG ? f : 0][REVG ? (R - 2 - 2 * r2 >= 0 ? R - 2 - 2 * r2 : 0) : 0] = v.y;
+                }
+            }
+        }
+    };
+
     double u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = 1.0;
@@ -190,7 +245,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     for (int f = 0; f < F; ++f) tops[f] = 1.0;
     double topprev = 1.0;
     // static kernel, pre-scaled by kscale = 4^-d / sqrt(12): k at the newest column; column differences
-    // d[j] = k[j+1] - k[j] at the stencil columns c, c+1, c+2
+    // d[j] = k[j+1] - k[j] at the stencil columns c, c+1, c+2 (REV_GRAD: k itself at those columns, because the
+    // gradient epilogue needs k[., c] bit-for-bit independent of the neighbouring pairs of the stream)
     double klast[RC], dA[RC], dB[RC], dC[RC];
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) klast[rc] = dA[rc] = dB[rc] = dC[rc] = 0.0;
@@ -202,13 +258,35 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         constexpr int Q = decltype(qc)::value;    // exchange buffer of this step
         // next step's stencil column is c+1: lane-1 needs this lane's first-row d[c+1] = dC as of NOW (made
         // one step ago), so this exchange does not wait for this step's production
-        sts_f64<Q * DXQ>(dxb, dC[0]);
+        sts_f64<Q * DXQ>(dxb, REVG ? klast[0] - dC[0] : dC[0]);
+        const bool real_col = sjob >= 0 && c < N - 1;
+        if (REVG && !PREF) load_fw(sjob, c);
+        double kc[RC];                            // REV_GRAD: k at (own node rows, node column c)
+        double up_c = 0.0, up_c1 = 0.0;           // REV_GRAD: S of lane-1's last coarse row at columns c, c-1
+        double sacc2[REVG ? RC : 1][REVG ? F : 1];
+        if (REVG) {
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                kc[rc] = dA[rc];                  // REV_GRAD keeps the k history itself (dA, dB, dC = k at columns c, c+1, c+2)
+#pragma unroll
+                for (int f = 0; f < F; ++f) sacc2[REVG ? rc : 0][REVG ? f : 0] = 0.0;
+            }
+            up_c = shfl_up1(Slast_cur);
+            up_c1 = shfl_up1(Slast_prev);
+            if (lane == 0) { up_c = 0.0; up_c1 = 0.0; }
+        }
+        double* srow = nullptr;                   // STORE: scratch row of fine column c * F, this lane's first row
+        if (STORE) srow = p.scratch + (((long)(real_col ? sjob : 0) * NNf + (long)(real_col ? c : 0) * F) * p.pitch + (long)lane * R);
         // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
         // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
         double ca[RC], cb[RC];
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) {
-            const double el = (rc + 1 < RC ? dA[rc + 1 < RC ? rc + 1 : rc] : dn) - dA[rc];
+            // REV_GRAD: the history holds k, so d[c] = k[c+1] - k[c] is formed here (same operands, same rounding
+            // as in the other modes, where it is formed once at production time)
+            const double dlo = REVG ? dB[rc] - dA[rc] : dA[rc];
+            const double dhi = rc + 1 < RC ? (REVG ? dB[rc + 1 < RC ? rc + 1 : rc] - dA[rc + 1 < RC ? rc + 1 : rc] : dA[rc + 1 < RC ? rc + 1 : rc]) : dn;
+            const double el = dhi - dlo;
             cb[rc] = fma(el, el, -1.0);
             ca[rc] = fma(el, p.sqrt3, cb[rc] + 2.0);
         }
@@ -235,6 +313,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     const int rm = r > 0 ? r - 1 : 0, fm = f > 0 ? f - 1 : 0;
                     const double diag = r == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rm] : U[rm][fm]);
                     tt[f] = cb[r >> LOGD] * diag;
+                    if (REVG) sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0] = fma(fw[REVG ? f : 0][REVG ? r : 0], diag, sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0]);
+                    if (STORE && (r & 1)) {
+                        // u[p, q] = the diagonal input of cell (p, q): rows r-1, r of fine column f as one 16-byte store
+                        const int r2 = r - 1, r2m = r2 > 0 ? r2 - 1 : 0;
+                        const double dprev = r2 == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[r2m] : U[r2m][fm]);
+                        if (real_col) *reinterpret_cast<double2*>(srow + (long)f * p.pitch + r2) = make_double2(dprev, diag);
+                    }
                 }
             }
 #pragma unroll
@@ -275,6 +360,35 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             }
         }
 
+        // ---- 2b. REV_GRAD: coarse sensitivities of column c -> second difference T -> W = T k -> accumulate ----
+        if (REVG) {
+            const bool dummy = c >= N - 1;
+            double Scur[RC];
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                double t = sacc2[REVG ? rc : 0][0];
+#pragma unroll
+                for (int f = 1; f < F; ++f) t += sacc2[REVG ? rc : 0][REVG ? f : 0];
+                const bool ok = !dummy && (lane * RC + rc < M - 1);
+                Scur[rc] = ok ? t * p.scale4 : 0.0;
+            }
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                const double uc = rc > 0 ? Scur[rc > 0 ? rc - 1 : 0] : up_c;
+                const double uc1 = rc > 0 ? Sprev[rc > 0 ? rc - 1 : 0] : up_c1;
+                const double T = (Scur[rc] - uc) - (Sprev[rc] - uc1);
+                const double W = KIND == KIND_RBF ? T * kc[rc] : T;
+                double* acc = gacc + (rc * (D + 1)) * 32 + lane;
+                acc[0] += W;
+                for (int k = 0; k < D; ++k) acc[(k + 1) * 32] = fma(W, __ldg(syp + 1 + k), acc[(k + 1) * 32]);
+            }
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) Sprev[rc] = Scur[rc];
+            Slast_prev = Slast_cur;
+            Slast_cur = Scur[RC - 1];
+            syp += Dp;
+        }
+
         // ---- 3. production: static kernel at node column e = c + LEAD (y row loaded one step ago) -----
         double dnew[RC];
 #pragma unroll
@@ -287,7 +401,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
             if (KIND == KIND_RBF) acc = exp_neg5(acc, etab, p);
-            dnew[rc] = acc - klast[rc];
+            dnew[rc] = REVG ? klast[rc] : acc - klast[rc];      // REV_GRAD: the history rotates k itself
             klast[rc] = acc;
         }
 
@@ -302,7 +416,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         ++c;
         yp += Dp;
         if (cc >= N - 2 || cc == pc) {
-            if (cc == N - 2) {
+            if (!REVG && cc == N - 2) {
                 // last coarse column done: u[MM, NN] is in the lane that owns grid row MM-1
                 if (sjob >= 0 && (unsigned)orc < (unsigned)RC) {
                     double res = u[F - 1];
@@ -320,6 +434,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 }
             }
             if (cc == N - 1) {
+                if (REVG) {
+                    // the pair is complete for this lane: emit its node rows (reversed order), clear the accumulators
+                    const long pi = p.job0 + sjob;                      // GRAM: a * B + b; BATCH: a
+                    const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + sxo);
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) {
+                        const int np = lane * RC + rc;                  // reversed node row
+                        double* acc = gacc + (rc * (D + 1)) * 32 + lane;
+                        if (sjob >= 0 && np < M) {
+                            double* gout = p.grad + (pi * M + (M - 1 - np)) * D;
+                            const double* xrw = sxb + (long)np * Dp;
+                            const double sW = acc[0];
+                            for (int k = 0; k < D; ++k) {
+                                const double gy = acc[(k + 1) * 32];
+                                gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                            }
+                        }
+                        for (int k = 0; k <= D; ++k) acc[k * 32] = 0.0;
+                    }
+                    sxo = xo; syo = yo;
+                    syp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + syo);
+                }
                 // node column N-1 has no coarse column: the step computed garbage; re-arm the boundary
                 // u[., 0] = 1 and hand the stencil stream the pair the production stream is in
 #pragma unroll
@@ -357,6 +493,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
 #pragma unroll
         for (int i = 0; i < DP2; ++i) yq[i] = ldg2(yp + 2 * i);
+        if (PREF) load_fw(sjob, c);               // the stored grid rows of the NEXT step
     };
 
 #pragma unroll 1

@@ -34,7 +34,7 @@ struct KArgs {
     double gscale;         // REV_GRAD: 2/sigma (RBF) or the linear scale factor
     // fwd5 (skb_fwd5.cuh): the static kernel is produced pre-scaled by kscale = 4^-d / sqrt(12); constants of
     // the coefficient polynomial and of the table-driven exp live here so that they are constant-bank operands
-    double kscale, sqrt3;
+    double kscale, sqrt3, inv_kscale;
     double ek, ehi, elo, e4, e3;
 };
 
@@ -88,5 +88,12 @@ bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1);
 // scale the static kernel is produced with on the fwd5 path (Linear: folded into the prepared X rows)
 double fwd5_kscale(int logd);
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st);
+// adjoint passes on the v5 kernel (MODE_FWD_STORE / MODE_REV_GRAD of skb_fwd5.cuh): one warp per pair, even strips
+bool adjoint5_applies(int kind, int M, int N, int D, int logd, bool s1);
+int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st);
+int launch_group_adj5_rbf_store(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_adj5_rbf_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_adj5_lin_store(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_adj5_lin_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 
 }  // namespace skb
