@@ -80,6 +80,14 @@ __device__ __forceinline__ double lds_f64(unsigned base) {
     return a;
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one whole 32-byte sector per lane and instruction
+__device__ __forceinline__ void stg_f64x4(double* ptr, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ldg_f64x4(const double* ptr, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(ptr));
+}
+
 // NW warps (32 NW lanes) share one pair: warp w+1 continues the wavefront of warp w (lane 0 of warp w+1 is
 // "lane 32 (w+1)"); the two values that cross the warp boundary every step (bottom row of lane 31 going down,
 // d of the next warp's first row going up) go through double-buffered shared memory and one block barrier.
@@ -215,23 +223,45 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
             for (int r = 0; r < R; ++r) fw[REVG ? f : 0][REVG ? r : 0] = 0.0;
     }
-    // rows of the stored grid this lane reads for (job, column): reversed coordinates, each lane's R values of
-    // one fine column are contiguous (the lanes of a warp are at 32 different columns, so a sector is written
-    // and read by ONE lane within one step; a layout that spreads a lane's rows over the row to "coalesce" the
-    // warp was measured 2.3x slower: partial lines get evicted and read back)
+    // Layout of the stored grid (v5 adjoint): LANE-major, [job][forward lane t][fine column q][R rows] -- each
+    // lane streams through its own contiguous NNf * R doubles, forwards when storing, backwards when the
+    // reversed sweep reads them.  (The lanes of a warp sit at 32 different columns, so nothing coalesces across
+    // lanes anyway; the column-major layout of solver_kernel makes every lane touch a different 1 KB row per
+    // step -- one DRAM page activation per 32-64 bytes.  Measured at cfg4: see DESIGN.md.)
+    // The reversed lane t reads forward rows p0 .. p0 + R - 1, p0 = MMl - (t+1) R: they straddle two forward
+    // lanes when MMl is not a multiple of R; rows p0 < 0 (strip outside the grid) are skipped, their S is masked.
+    const long lane_stride = NNf * R, job_stride = 32 * lane_stride;
     auto load_fw = [&](int job_, int col_) {
         if (REVG) {
             const bool real = job_ >= 0 && col_ < N - 1;
-            const double* srow = p.scratch + (((long)(real ? job_ : 0) * NNf + (NNf - 1 - (long)(real ? col_ : 0) * F)) * p.pitch +
-                                              (MMl - (long)(lane + 1) * R));
+            const double* jb = p.scratch + (long)(real ? job_ : 0) * job_stride + (NNf - 1 - (long)(real ? col_ : 0) * F) * R;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
+                if (R % 4 == 0 && (MMl & 3) == 0) {
+                    // MMl a multiple of 4: the reversed strips line up with the 32-byte groups of the forward lanes
 #pragma unroll
-                for (int r2 = 0; r2 < R / 2; ++r2) {
-                    double2 v = make_double2(0.0, 0.0);
-                    if (real) v = *reinterpret_cast<const double2*>(srow - (long)f * p.pitch + 2 * r2);
-                    fw[REVG ? f : 0][REVG ? R - 1 - 2 * r2 : 0] = v.x;
-                    fw[REVG ? f : 0][REVG ? (R - 2 - 2 * r2 >= 0 ? R - 2 - 2 * r2 : 0) : 0] = v.y;
+                    for (int j = 0; j < R / 4; ++j) {
+                        const long p0 = MMl - (long)(lane + 1) * R + 4 * j;
+                        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+                        if (real && p0 >= 0 && !(p.band_row0 & 2))
+                            ldg_f64x4(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R), v0, v1, v2, v3);
+                        // forward rows p0 .. p0+3 are reversed rows R-1-4j .. R-4-4j of this lane's strip
+                        fw[REVG ? f : 0][REVG ? R - 1 - 4 * j : 0] = v0;
+                        fw[REVG ? f : 0][REVG ? (R - 2 - 4 * j >= 0 ? R - 2 - 4 * j : 0) : 0] = v1;
+                        fw[REVG ? f : 0][REVG ? (R - 3 - 4 * j >= 0 ? R - 3 - 4 * j : 0) : 0] = v2;
+                        fw[REVG ? f : 0][REVG ? (R - 4 - 4 * j >= 0 ? R - 4 - 4 * j : 0) : 0] = v3;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < R / 2; ++j) {
+                        const long p0 = MMl - (long)(lane + 1) * R + 2 * j;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (real && p0 >= 0 && !(p.band_row0 & 2))
+                            v = *reinterpret_cast<const double2*>(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R));
+                        // forward rows p0, p0 + 1 are reversed rows R-1-2j, R-2-2j of this lane's strip
+                        fw[REVG ? f : 0][REVG ? R - 1 - 2 * j : 0] = v.x;
+                        fw[REVG ? f : 0][REVG ? (R - 2 - 2 * j >= 0 ? R - 2 - 2 * j : 0) : 0] = v.y;
+                    }
                 }
             }
         }
@@ -275,8 +305,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             up_c1 = shfl_up1(Slast_prev);
             if (lane == 0) { up_c = 0.0; up_c1 = 0.0; }
         }
-        double* srow = nullptr;                   // STORE: scratch row of fine column c * F, this lane's first row
-        if (STORE) srow = p.scratch + (((long)(real_col ? sjob : 0) * NNf + (long)(real_col ? c : 0) * F) * p.pitch + (long)lane * R);
+        double* srow = nullptr;                   // STORE: this lane's R values of fine column c * F
+        if (STORE) srow = p.scratch + (long)(real_col ? sjob : 0) * job_stride + (long)lane * lane_stride + (long)(real_col ? c : 0) * F * R;
         // ---- 1. stencil coefficients of coarse column c ---------------------------------------------
         // e = g / sqrt(12) (g = the refined increment):  -b = e^2 - 1,  a = 1 + g/2 + g^2/12 = sqrt(3) e + (2 - b)
         double ca[RC], cb[RC];
@@ -314,11 +344,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     const double diag = r == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rm] : U[rm][fm]);
                     tt[f] = cb[r >> LOGD] * diag;
                     if (REVG) sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0] = fma(fw[REVG ? f : 0][REVG ? r : 0], diag, sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0]);
-                    if (STORE && (r & 1)) {
-                        // u[p, q] = the diagonal input of cell (p, q): rows r-1, r of fine column f as one 16-byte store
-                        const int r2 = r - 1, r2m = r2 > 0 ? r2 - 1 : 0;
-                        const double dprev = r2 == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[r2m] : U[r2m][fm]);
-                        if (real_col) *reinterpret_cast<double2*>(srow + (long)f * p.pitch + r2) = make_double2(dprev, diag);
+                    if (STORE && (R % 4 == 0 ? (r & 3) == 3 : (r & 1))) {
+                        // u[p, q] = the diagonal input of cell (p, q); a lane's rows of one fine column leave as whole
+                        // 32-byte sectors (R % 4 == 0) or 16-byte pairs, as soon as the last of them is known
+                        auto dg = [&](int rr) {
+                            const int rrm = rr > 0 ? rr - 1 : 0;
+                            return rr == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rrm] : U[rrm][fm]);
+                        };
+                        if (real_col && !(p.band_row0 & 1)) {
+                            if (R % 4 == 0) stg_f64x4(srow + f * R + (r - 3), dg(r - 3 >= 0 ? r - 3 : 0), dg(r - 2 >= 0 ? r - 2 : 0), dg(r - 1), diag);
+                            else *reinterpret_cast<double2*>(srow + f * R + (r - 1)) = make_double2(dg(r - 1), diag);
+                        }
                     }
                 }
             }
