@@ -211,7 +211,6 @@ bool adjoint5_applies(int kind, int M, int N, int D, int logd, bool s1) {
 int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     const int rcp = coarse_rows_per_lane(args.M);
     fill_v5_constants(args, logd);
-    { const char* e = getenv("SKB_DBG"); args.band_row0 = e ? atoi(e) : 0; }
     args.pitch = 32L * (rcp << logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     static_assert(MODE == 0 || STORE || REVG, "unknown mode");
     static_assert(MODE == 0 || (NW == 1 && LOGD >= 1), "the adjoint modes use one warp per pair and 16-byte grid rows");
     constexpr bool PREF = REVG && (F * R <= 8);  // stored grid read one step ahead into registers
+    constexpr bool GREG = REVG && (RC * DP2 <= 4);   // gradient accumulators in registers instead of shared memory
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
@@ -216,8 +217,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) Sprev[rc] = 0.0;
     double fw[REVG ? F : 1][REVG ? R : 1];        // forward values of the cells of this step (reversed row order)
+    double ga[GREG ? RC : 1][GREG ? Dp : 1];      // GREG: [coarse row][0: sum of W; 1..D: sum of W y_k]
+#pragma unroll
+    for (int rc = 0; rc < (GREG ? RC : 1); ++rc)
+#pragma unroll
+        for (int e2 = 0; e2 < (GREG ? Dp : 1); ++e2) ga[rc][e2] = 0.0;
     if (REVG) {
-        for (int i = 0; i < RC * (D + 1); ++i) gacc[i * 32 + lane] = 0.0;
+        if (!GREG) for (int i = 0; i < RC * (D + 1); ++i) gacc[i * 32 + lane] = 0.0;
 #pragma unroll
         for (int f = 0; f < F; ++f)
 #pragma unroll
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     for (int j = 0; j < R / 4; ++j) {
                         const long p0 = MMl - (long)(lane + 1) * R + 4 * j;
                         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                        if (real && p0 >= 0 && !(p.band_row0 & 2))
+                        if (real && p0 >= 0))
                             ldg_f64x4(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R), v0, v1, v2, v3);
                         // forward rows p0 .. p0+3 are reversed rows R-1-4j .. R-4-4j of this lane's strip
                         fw[REVG ? f : 0][REVG ? R - 1 - 4 * j : 0] = v0;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     for (int j = 0; j < R / 2; ++j) {
                         const long p0 = MMl - (long)(lane + 1) * R + 2 * j;
                         double2 v = make_double2(0.0, 0.0);
-                        if (real && p0 >= 0 && !(p.band_row0 & 2))
+                        if (real && p0 >= 0))
                             v = *reinterpret_cast<const double2*>(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R));
                         // forward rows p0, p0 + 1 are reversed rows R-1-2j, R-2-2j of this lane's strip
                         fw[REVG ? f : 0][REVG ? R - 1 - 2 * j : 0] = v.x;
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                             const int rrm = rr > 0 ? rr - 1 : 0;
                             return rr == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rrm] : U[rrm][fm]);
                         };
-                        if (real_col && !(p.band_row0 & 1)) {
+                        if (real_col) {
                             if (R % 4 == 0) stg_f64x4(srow + f * R + (r - 3), dg(r - 3 >= 0 ? r - 3 : 0), dg(r - 2 >= 0 ? r - 2 : 0), dg(r - 1), diag);
                             else *reinterpret_cast<double2*>(srow + f * R + (r - 1)) = make_double2(dg(r - 1), diag);
                         }
@@ -414,9 +420,19 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 const double uc1 = rc > 0 ? Sprev[rc > 0 ? rc - 1 : 0] : up_c1;
                 const double T = (Scur[rc] - uc) - (Sprev[rc] - uc1);
                 const double W = KIND == KIND_RBF ? T * kc[rc] : T;
-                double* acc = gacc + (rc * (D + 1)) * 32 + lane;
-                acc[0] += W;
-                for (int k = 0; k < D; ++k) acc[(k + 1) * 32] = fma(W, __ldg(syp + 1 + k), acc[(k + 1) * 32]);
+                if (GREG) {
+                    // the prepared y row is (norm term, y_1 .. y_D, 0 ...): slot 0 accumulates W itself
+#pragma unroll
+                    for (int i = 0; i < DP2; ++i) {
+                        const double2 yv = ldg2(syp + 2 * i);
+                        ga[GREG ? rc : 0][GREG ? 2 * i : 0] = fma(W, i == 0 ? 1.0 : yv.x, ga[GREG ? rc : 0][GREG ? 2 * i : 0]);
+                        ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = fma(W, yv.y, ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0]);
+                    }
+                } else {
+                    double* acc = gacc + (rc * (D + 1)) * 32 + lane;
+                    acc[0] += W;
+                    for (int k = 0; k < D; ++k) acc[(k + 1) * 32] = fma(W, __ldg(syp + 1 + k), acc[(k + 1) * 32]);
+                }
             }
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) Sprev[rc] = Scur[rc];
@@ -481,13 +497,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         if (sjob >= 0 && np < M) {
                             double* gout = p.grad + (pi * M + (M - 1 - np)) * D;
                             const double* xrw = sxb + (long)np * Dp;
-                            const double sW = acc[0];
-                            for (int k = 0; k < D; ++k) {
-                                const double gy = acc[(k + 1) * 32];
-                                gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                            if (GREG) {
+                                const double sW = ga[GREG ? rc : 0][0];
+#pragma unroll
+                                for (int k = 0; k < Dp - 1; ++k)
+                                    if (k < D) {
+                                        const double gy = ga[GREG ? rc : 0][GREG ? k + 1 : 0];
+                                        gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                    }
+                            } else {
+                                const double sW = acc[0];
+                                for (int k = 0; k < D; ++k) {
+                                    const double gy = acc[(k + 1) * 32];
+                                    gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                }
                             }
                         }
-                        for (int k = 0; k <= D; ++k) acc[k * 32] = 0.0;
+                        if (GREG) {
+#pragma unroll
+                            for (int e2 = 0; e2 < (GREG ? Dp : 1); ++e2) ga[GREG ? rc : 0][e2] = 0.0;
+                        } else {
+                            for (int k = 0; k <= D; ++k) acc[k * 32] = 0.0;
+                        }
                     }
                     sxo = xo; syo = yo;
                     syp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + syo);
