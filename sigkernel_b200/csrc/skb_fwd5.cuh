@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     for (int j = 0; j < R / 4; ++j) {
                         const long p0 = MMl - (long)(lane + 1) * R + 4 * j;
                         double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-                        if (real && p0 >= 0))
+                        if (real && p0 >= 0)
                             ldg_f64x4(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R), v0, v1, v2, v3);
                         // forward rows p0 .. p0+3 are reversed rows R-1-4j .. R-4-4j of this lane's strip
                         fw[REVG ? f : 0][REVG ? R - 1 - 4 * j : 0] = v0;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     for (int j = 0; j < R / 2; ++j) {
                         const long p0 = MMl - (long)(lane + 1) * R + 2 * j;
                         double2 v = make_double2(0.0, 0.0);
-                        if (real && p0 >= 0))
+                        if (real && p0 >= 0)
                             v = *reinterpret_cast<const double2*>(jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R));
                         // forward rows p0, p0 + 1 are reversed rows R-1-2j, R-2-2j of this lane's strip
                         fw[REVG ? f : 0][REVG ? R - 1 - 2 * j : 0] = v.x;
