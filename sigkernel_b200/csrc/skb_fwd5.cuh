@@ -88,6 +88,15 @@ __device__ __forceinline__ void ldg_f64x4(const double* ptr, double& a, double& 
     asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(ptr));
 }
 
+// cp.async 16 bytes global -> shared, zero-filled when !valid (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 // NW warps (32 NW lanes) share one pair: warp w+1 continues the wavefront of warp w (lane 0 of warp w+1 is
 // "lane 32 (w+1)"); the two values that cross the warp boundary every step (bottom row of lane 31 going down,
 // d of the next warp's first row going up) go through double-buffered shared memory and one block barrier.
@@ -106,7 +115,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr bool STORE = MODE == MODE_FWD_STORE, REVG = MODE == MODE_REV_GRAD;
     static_assert(MODE == 0 || STORE || REVG, "unknown mode");
     static_assert(MODE == 0 || (NW == 1 && LOGD >= 1), "the adjoint modes use one warp per pair and 16-byte grid rows");
-    constexpr bool PREF = REVG && (F * R <= 8);  // stored grid read one step ahead into registers
+    // REV_GRAD reads the stored grid through a per-lane cp.async ring in shared memory, DEPTH steps ahead (the
+    // lane-major layout makes every lane's stream contiguous): the loads of a whole DEPTH-step window are in
+    // flight per lane, which is what it takes to cover the loaded HBM latency (measured ~3 us) -- one step ahead
+    // in registers was not enough (long_scoreboard 5.2 stalled warps per issue).
+    constexpr bool STAGE = REVG && (F * R <= 16);
+    constexpr int DEPTH = (F * R <= 8) ? 4 : 2;
+    constexpr int NP = F * R / 2;                // 16-byte pieces per lane and step
     constexpr bool GREG = REVG && (RC * DP2 <= 4);   // gradient accumulators in registers instead of shared memory
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
@@ -273,6 +288,47 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
     };
 
+    // staging ring: [slot][piece k = f * R/2 + j][lane] 16-byte entries, behind the gradient accumulators
+    const unsigned stg0 = STAGE ? (unsigned)__cvta_generic_to_shared(gacc + (size_t)RC * (D + 1) * 32) + lane * 16 : 0;
+    int sq = 0;                                   // ring slot of the current step
+    auto stage_issue = [&](int slot, int job_, int col_) {
+        if (STAGE) {
+            const bool real = job_ >= 0 && col_ >= 0 && col_ < N - 1;
+            const double* jb = p.scratch + (long)(real ? job_ : 0) * job_stride + (NNf - 1 - (long)(real ? col_ : 0) * F) * R;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int j = 0; j < R / 2; ++j) {
+                    const long p0 = MMl - (long)(lane + 1) * R + 2 * j;
+                    const bool ok = real && p0 >= 0;
+                    const double* src = ok ? jb + (p0 / R) * lane_stride - (long)f * R + (p0 % R) : p.scratch;
+                    cp_async16(stg0 + ((slot * NP + f * (R / 2) + j) * 32) * 16, src, ok);
+                }
+            }
+            cp_async_commit();
+        }
+    };
+    auto stage_consume = [&](int slot) {
+        if (STAGE) {
+            cp_async_wait<DEPTH - 1>();
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+#pragma unroll
+                for (int j = 0; j < R / 2; ++j) {
+                    double vx, vy;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(stg0 + ((slot * NP + f * (R / 2) + j) * 32) * 16) : "memory");
+                    // forward rows p0, p0 + 1 are reversed rows R-1-2j, R-2-2j of this lane's strip
+                    fw[REVG ? f : 0][REVG ? R - 1 - 2 * j : 0] = vx;
+                    fw[REVG ? f : 0][REVG ? (R - 2 - 2 * j >= 0 ? R - 2 - 2 * j : 0) : 0] = vy;
+                }
+            }
+        }
+    };
+    if (STAGE) {
+#pragma unroll
+        for (int d0 = 0; d0 < DEPTH; ++d0) stage_issue(d0, -1, 0);     // the first DEPTH steps are virtual for every lane
+    }
+
     double u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = 1.0;
@@ -296,7 +352,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         // one step ago), so this exchange does not wait for this step's production
         sts_f64<Q * DXQ>(dxb, REVG ? klast[0] - dC[0] : dC[0]);
         const bool real_col = sjob >= 0 && c < N - 1;
-        if (REVG && !PREF) load_fw(sjob, c);
+        if (REVG && !STAGE) load_fw(sjob, c);
+        if (STAGE) stage_consume(sq);
         double kc[RC];                            // REV_GRAD: k at (own node rows, node column c)
         double up_c = 0.0, up_c1 = 0.0;           // REV_GRAD: S of lane-1's last coarse row at columns c, c-1
         double sacc2[REVG ? RC : 1][REVG ? F : 1];
@@ -560,7 +617,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
 #pragma unroll
         for (int i = 0; i < DP2; ++i) yq[i] = ldg2(yp + 2 * i);
-        if (PREF) load_fw(sjob, c);               // the stored grid rows of the NEXT step
+        if (STAGE) {
+            // refill the slot just consumed with the rows of the step DEPTH ahead: column c + DEPTH - 1 of this
+            // pair, or -- past the dummy column N-1 -- of the pair the production stream is already in
+            const int cT = c + DEPTH - 1;
+            stage_issue(sq, cT >= N ? pjob : sjob, cT >= N ? cT - N : (cT == N - 1 ? -1 : cT));
+            sq = sq + 1 == DEPTH ? 0 : sq + 1;
+        }
     };
 
 #pragma unroll 1
