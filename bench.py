@@ -340,7 +340,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": Xh.numel() * 8 + Yh.numel() * 8, "d2h_bytes_per_step": Gh.numel() * 8,
                     "ms_per_step": t_e2e / args.steps * 1e3,
                     "api": "SigKernel(RBFKernel(0.5), 2).compute_Gram(X.cuda(), Y.cuda()) + .cpu()"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 2 * args.steps,          # per step: prep2_kernel (paths + queue reset) and fwd5_kernel
             "roofline": roofline,
             "cpu_baseline": cpu,
         }

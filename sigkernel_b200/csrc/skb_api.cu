@@ -131,6 +131,7 @@ static int run_generic_forward(int src_kind, KArgs a, int d, bool exact, long nj
             const long row0 = band * H;
             const long hb = MMf - row0 < H ? MMf - row0 : H;
             b.Ks = inc_src;
+            b.counter_clean = 0;                     // one launch per band: each needs its own reset
             b.Xp = b.Yp = nullptr;
             b.M = (int)hb + 1;
             b.N = (int)NNf + 1;
@@ -233,13 +234,12 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
                       (size_t)A * M * padded_dim(D) * sizeof(double) < ((size_t)1 << 32) &&
                       (size_t)B * N * padded_dim(D) * sizeof(double) < ((size_t)1 << 32);   // 32-bit byte offsets in the job ring
     if (use5 && kind == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on that path
-    rc = launch_prep(X, io_dtype, Xp, nullptr, A, M, D, Dp, cx, nsc, st);
-    if (rc) return rc;
-    rc = launch_prep(Y, io_dtype, Yp, nullptr, B, N, D, Dp, 1.0, nsc, st);
+    rc = launch_prep2(X, Y, io_dtype, Xp, nullptr, Yp, nullptr, A, M, B, N, D, Dp, cx, nsc, counter, st);
     if (rc) return rc;
 
     KArgs a = base_args(A, B, M, N, dyadic_order, scheme, pairs);
     a.Xp = Xp; a.Yp = Yp; a.out = out; a.counter = counter;
+    a.counter_clean = 1;                 // zeroed by the preparation kernel
     const long nj = njobs_of(A, B, pairs);
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
@@ -342,9 +342,7 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     const bool v5 = adjoint5_applies(kind5, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
                     (size_t)A * M * Dp * sizeof(double) < ((size_t)1 << 32) && (size_t)B * N * Dp * sizeof(double) < ((size_t)1 << 32);
     if (v5 && kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on the v5 path
-    rc = launch_prep(X, io_dtype, Xp, Xr, A, M, D, Dp, cx, nsc, st);
-    if (rc) return rc;
-    rc = launch_prep(Y, io_dtype, Yp, Yr, B, N, D, Dp, 1.0, nsc, st);
+    rc = launch_prep2(X, Y, io_dtype, Xp, Xr, Yp, Yr, A, M, B, N, D, Dp, cx, nsc, nullptr, st);
     if (rc) return rc;
 
     const long nj = njobs_of(A, B, pairs);

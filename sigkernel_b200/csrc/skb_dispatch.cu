@@ -34,6 +34,53 @@ __global__ void prep_kernel(const T* __restrict__ X, double* __restrict__ Xp, do
     }
 }
 
+// X and Y in ONE launch, which also zeroes the job-queue counter of the solver launch that follows (a forward
+// call is then two launches, not four: at 64x64 pairs of 32 points the launches were a third of the time)
+template <typename T>
+__global__ void prep2_kernel(const T* __restrict__ X, const T* __restrict__ Y, double* __restrict__ Xp,
+                             double* __restrict__ Xr, double* __restrict__ Yp, double* __restrict__ Yr, long rowsX,
+                             long rowsY, int M, int N, int D, int Dp, double cx, double nscale, unsigned int* counter) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0 && counter) *counter = 0u;
+    if (r >= rowsX + rowsY) return;
+    const bool isx = r < rowsX;
+    const long rr = isx ? r : r - rowsX;
+    const int len = isx ? M : N;
+    const T* x = (isx ? X : Y) + rr * D;
+    double* P = isx ? Xp : Yp;
+    double* Prv = isx ? Xr : Yr;
+    const double c = isx ? cx : 1.0;
+    const long bi = rr / len;
+    const int li = (int)(rr - bi * len);
+    double* o = P + rr * Dp;
+    double* orv = Prv ? Prv + (bi * len + (len - 1 - li)) * Dp : nullptr;
+    double n = 0.0;
+    for (int k = 0; k < D; ++k) {
+        const double v = (double)x[k];
+        n = fma(v, v, n);
+        o[1 + k] = v * c;
+        if (orv) orv[1 + k] = v * c;
+    }
+    o[0] = n * nscale;
+    if (orv) orv[0] = n * nscale;
+    for (int k = D + 1; k < Dp; ++k) {
+        o[k] = 0.0;
+        if (orv) orv[k] = 0.0;
+    }
+}
+
+int launch_prep2(const void* X, const void* Y, int dtype, double* Xp, double* Xr, double* Yp, double* Yr, long A, int M,
+                 long B, int N, int D, int Dp, double cx, double nscale, unsigned int* counter, cudaStream_t st) {
+    const long rowsX = A * M, rowsY = B * N;
+    const int tb = 128;
+    const unsigned grid = (unsigned)((rowsX + rowsY + tb - 1) / tb);
+    if (dtype == SKB_F64)
+        prep2_kernel<double><<<grid, tb, 0, st>>>((const double*)X, (const double*)Y, Xp, Xr, Yp, Yr, rowsX, rowsY, M, N, D, Dp, cx, nscale, counter);
+    else
+        prep2_kernel<float><<<grid, tb, 0, st>>>((const float*)X, (const float*)Y, Xp, Xr, Yp, Yr, rowsX, rowsY, M, N, D, Dp, cx, nscale, counter);
+    return check_launch();
+}
+
 int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch, int len, int D, int Dp,
                 double c, double nscale, cudaStream_t st) {
     const long rows = batch * len;
@@ -213,7 +260,7 @@ int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     fill_v5_constants(args, logd);
     args.pitch = 32L * (rcp << logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
-    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    int rc = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;
     const bool rbf = kind == KIND_RBF;
     if (mode == 1) return rbf ? launch_group_adj5_rbf_store(rcp, logd, args.Dp / 2, args, st) : launch_group_adj5_lin_store(rcp, logd, args.Dp / 2, args, st);
@@ -227,7 +274,7 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
     fill_v5_constants(args, logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
-    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    int rc = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;
     if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
     typedef int (*fwd5_fn)(int, int, int, const KArgs&, cudaStream_t);
@@ -247,7 +294,7 @@ int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStre
     args.rcstar = (args.M - 2) % rcp;
     args.pitch = 32L * (rcp << logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
-    int rc = check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    int rc = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;
     int dp2 = 0;
     if (kind == KIND_RBF || kind == KIND_LINEAR) {

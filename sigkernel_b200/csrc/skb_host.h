@@ -15,6 +15,7 @@ struct KArgs {
     double* S;             // REV_S: coarse sensitivities (pairs, M-1, N-1)
     double* grad;          // REV_GRAD: per-point gradients (pairs, M, D)
     unsigned int* counter; // job queue (zeroed before the launch)
+    int counter_clean;     // host side: the counter was already zeroed by the preparation kernel (first launch of a call)
     long job0;             // first job of this launch in the pair enumeration
     long pitch;            // scratch row pitch in doubles (32 * R)
     int njobs;             // jobs of this launch
@@ -47,6 +48,8 @@ void set_profile_events(void* start, void* stop);
 int get_warps_per_sm();
 int sm_count();
 
+int launch_prep2(const void* X, const void* Y, int dtype, double* Xp, double* Xr, double* Yp, double* Yr, long A, int M,
+                 long B, int N, int D, int Dp, double cx, double nscale, unsigned int* counter, cudaStream_t st);
 int launch_prep(const void* X, int dtype, double* Xp, double* Xp_rev, long batch, int len, int D, int Dp,
                 double c, double nscale, cudaStream_t st);
 
