@@ -76,6 +76,17 @@ void skb_set_profile_events(void* start_event, void* stop_event);
  * instructions per launch, timed by the caller with CUDA events on `stream`.  threads <= 256. */
 int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream);
 
+/* Which kernel family a call would use (host-side dispatch only, no GPU work; for tests and diagnostics):
+ *   skb_forward_plan  (skb_sigkernel_fwd):      0 = generic row-band sweep of the fine grid (any shape),
+ *                                               1 = register-resident solver_kernel (v4),
+ *                                               5 / 6 / 7 = fwd5_kernel with 1 / 2 / 4 warps per pair;
+ *   skb_adjoint_plan  (skb_sigkernel_fwd_bwd): -4 (SKB_ERR_UNSUPPORTED) = shape not covered by the backward,
+ *                                               1 = solver_kernel store / reversed modes (v4),
+ *                                               5 = fwd5_kernel store / reversed modes.
+ * Negative values are SKB_ERR_* codes for bad arguments. */
+int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
+int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
+
 /* ---- workspaces -------------------------------------------------------------------
  * Every compute entry point takes a caller-owned device scratch buffer (256-byte aligned) that
  * holds the job-queue counter, the prepared paths and (backward) the forward solution grids.

@@ -26,6 +26,8 @@ SYMBOLS = {
     "skb_set_warps_per_sm": (None, [_i]),
     "skb_set_profile_events": (None, [_vp, _vp]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
+    "skb_forward_plan": (_i, [_i, _i, _i, _i, _i, _i]),
+    "skb_adjoint_plan": (_i, [_i, _i, _i, _i, _i, _i]),
     "skb_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_aux_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -176,6 +176,27 @@ int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
 void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
+int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme) {
+    if (M < 2 || N < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1)) {
+        const int nw = fwd5_warps_per_pair(M, dyadic_order);
+        return nw == 1 ? 5 : (nw == 2 ? 6 : 7);
+    }
+    return solver_rows_per_lane(M, dyadic_order) >= 0 ? 1 : 0;
+}
+
+int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme) {
+    if (M < 2 || N < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (solver_rows_per_lane(M, dyadic_order) < 0) return SKB_ERR_UNSUPPORTED;
+    return adjoint5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) ? 5 : 1;
+}
+
 size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return 0;
     const size_t Dp = (size_t)padded_dim(D);

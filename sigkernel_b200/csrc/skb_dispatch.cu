@@ -219,6 +219,8 @@ static int fwd5_plan(int M, int logd, int* rc_out) {
     return 0;
 }
 
+int fwd5_warps_per_pair(int M, int logd) { return fwd5_plan(M, logd, nullptr); }
+
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     if (!use_fwd5() || s1 || N < 4) return false;
     if (kind != KIND_RBF && kind != KIND_LINEAR) return false;

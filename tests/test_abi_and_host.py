@@ -153,3 +153,29 @@ def test_host_gradient_helpers_match_oracle():
     hi, lo = _second_diff_x(Kh, Ks)
     gp = _grad_points_from_sensitivity(S, hi, lo) / _H_FD
     assert np.max(np.abs(gp.numpy() - gp_ref.numpy())) <= 1e-9 * np.max(np.abs(gp_ref.numpy()))
+
+
+def test_dispatch_plans_for_the_baseline_configs():
+    """Host-side dispatch (no GPU): every BASELINE config takes the v5 kernels; odd shapes fall back as documented."""
+    lib = skb._lib.lib
+    LIN, RBF, S2, S1 = 0, 1, 0, 1
+    # forward: M, N, D, d, kind, scheme -> plan
+    assert lib.skb_forward_plan(10, 10, 2, 0, LIN, S2) == 5      # cfg1
+    assert lib.skb_forward_plan(32, 32, 3, 1, RBF, S2) == 5      # cfg2
+    assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S2) == 5      # cfg3 (headline)
+    assert lib.skb_forward_plan(64, 64, 3, 1, RBF, S2) == 5      # cfg4 forward
+    assert lib.skb_forward_plan(128, 128, 8, 2, RBF, S2) == 6    # cfg5: two warps per pair
+    assert lib.skb_forward_plan(250, 9, 3, 2, RBF, S2) == 7      # four warps per pair
+    assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S1) == 1      # _naive_solver: v4 kernel
+    assert lib.skb_forward_plan(64, 3, 5, 2, RBF, S2) == 1       # len_y < 4: v4 kernel
+    assert lib.skb_forward_plan(64, 64, 12, 2, RBF, S2) == 1     # dim + 1 > 10: generic-width v4 kernel
+    assert lib.skb_forward_plan(1000, 6, 2, 0, RBF, S2) == 0     # beyond the register-resident kernels: row bands
+    assert lib.skb_forward_plan(1, 6, 2, 0, RBF, S2) == -1
+    assert lib.skb_forward_plan(8, 6, 2, 0, 9, S2) == -2
+    # backward
+    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S2) == 5      # cfg4
+    assert lib.skb_adjoint_plan(64, 64, 5, 2, RBF, S2) == 5
+    assert lib.skb_adjoint_plan(40, 70, 8, 0, RBF, S2) == 1      # dyadic order 0: v4 adjoint kernels
+    assert lib.skb_adjoint_plan(128, 128, 8, 2, RBF, S2) == 1    # more than one warp per pair: v4
+    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S1) == 1
+    assert lib.skb_adjoint_plan(1000, 6, 2, 0, RBF, S2) == -4    # backward not covered (SKB_ERR_UNSUPPORTED)
