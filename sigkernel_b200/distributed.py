@@ -16,6 +16,23 @@ def row_block(n_rows, rank, world):
     return lo, lo + q + (1 if rank < r else 0)
 
 
+class _GatherRows(torch.autograd.Function):
+    """All-gather of equally sized row blocks that autograd can cross: the backward of rank r is simply rows
+    [lo_r, hi_r) of the upstream gradient -- no collective, PROVIDED every rank evaluates the same loss on the
+    gathered matrix (the usual data-parallel situation: G is replicated, so is d loss / d G)."""
+
+    @staticmethod
+    def forward(ctx, block, lo, hi, n_rows, group):
+        ctx.lo, ctx.hi = lo, hi
+        G = torch.empty((n_rows, block.shape[1]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(G, block.contiguous(), group=group)
+        return G
+
+    @staticmethod
+    def backward(ctx, grad_G):
+        return grad_G[ctx.lo:ctx.hi], None, None, None, None
+
+
 def sharded_gram(X, Y, gram_fn, group=None, gather=True):
     """G = gram_fn(X, Y) computed as row blocks: rank r solves gram_fn(X[lo_r:hi_r], Y).
 
@@ -33,6 +50,10 @@ def sharded_gram(X, Y, gram_fn, group=None, gather=True):
     if not gather:
         return block
     if A % world == 0:
+        if block.requires_grad:
+            # gradients w.r.t. X flow back into this rank's rows of X only (each rank owns the complete rows a
+            # of grad_points[a, :, :, :]); all-reduce X.grad afterwards if every rank needs all rows
+            return _GatherRows.apply(block, lo, hi, A, group)
         G = torch.empty((A, B), dtype=block.dtype, device=block.device)
         dist.all_gather_into_tensor(G, block.contiguous(), group=group)
         return G
@@ -50,5 +71,13 @@ def sharded_gram(X, Y, gram_fn, group=None, gather=True):
 
 
 def compute_Gram_sharded(sig_kernel, X, Y, group=None, gather=True):
-    """`SigKernel.compute_Gram(X, Y)` sharded over the ranks of `group` (forward only)."""
+    """`SigKernel.compute_Gram(X, Y)` sharded over the ranks of `group`.  Differentiable w.r.t. X when the batch
+    divides evenly: after `loss(G).backward()` rank r holds d loss / d X in rows [lo_r, hi_r) of `X.grad` (zeros
+    elsewhere); `all_reduce_grad_rows(X.grad)` replicates the full gradient if it is needed everywhere."""
     return sharded_gram(X, Y, lambda x, y: sig_kernel.compute_Gram(x, y, sym=False), group, gather)
+
+
+def all_reduce_grad_rows(grad, group=None):
+    """Sum the per-rank row-sparse gradients of a sharded backward so that every rank holds all rows."""
+    dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    return grad

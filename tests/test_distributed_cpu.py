@@ -63,3 +63,41 @@ def test_sharded_gram_world2_gloo(A):
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _worker_grad(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sigkernel_b200.distributed import all_reduce_grad_rows, sharded_gram
+        g = torch.Generator().manual_seed(0)
+        X = torch.rand((6, 5, 2), dtype=torch.float64, generator=g)
+        Y = torch.rand((4, 7, 2), dtype=torch.float64, generator=g)
+        w = torch.rand((6, 4), dtype=torch.float64, generator=g)
+        fn = lambda x, y: torch.einsum('amd,bnd->ab', torch.tanh(x), y)      # any differentiable stand-in for the solve
+        Xr = X.clone().requires_grad_(True)
+        (fn(Xr, Y) * w).sum().backward()
+        Xs = X.clone().requires_grad_(True)
+        G = sharded_gram(Xs, Y, fn)
+        (G * w).sum().backward()
+        lo, hi = row_block(6, rank, world)
+        own = torch.allclose(Xs.grad[lo:hi], Xr.grad[lo:hi], rtol=0, atol=1e-14)
+        rest = torch.count_nonzero(Xs.grad[:lo]) == 0 and torch.count_nonzero(Xs.grad[hi:]) == 0
+        full = all_reduce_grad_rows(Xs.grad.clone())
+        out_q.put((rank, bool(own and rest and torch.allclose(full, Xr.grad, rtol=0, atol=1e-14) and torch.equal(G.detach(), fn(X, Y)))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gram_backward_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_grad, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(q.get(timeout=5) for _ in range(2)) == {0: True, 1: True}
