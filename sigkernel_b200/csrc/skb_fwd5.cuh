@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // lane-major layout makes every lane's stream contiguous): the loads of a whole DEPTH-step window are in
     // flight per lane, which is what it takes to cover the loaded HBM latency (measured ~3 us) -- one step ahead
     // in registers was not enough (long_scoreboard 5.2 stalled warps per issue).
-    constexpr bool STAGE = REVG && (F * R <= 16);
-    constexpr int DEPTH = (F * R <= 8) ? 4 : 2;
+    constexpr bool STAGE = REVG && (F * R <= 32);
+    constexpr int DEPTH = (F * R <= 8) ? 4 : (F * R <= 16 ? 2 : 1);
     constexpr int NP = F * R / 2;                // 16-byte pieces per lane and step
-    constexpr bool GREG = REVG && (RC * DP2 <= 4);   // gradient accumulators in registers instead of shared memory
+    constexpr bool GREG = REVG && (RC * DP2 <= 6);   // gradient accumulators in registers instead of shared memory
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)

@@ -12,7 +12,7 @@ static int launch_adj5(const KArgs& a, cudaStream_t st) {
     long nb = (long)sm_count() * wpsm;
     if (nb > a.njobs) nb = a.njobs;
     constexpr int FR = (RC << LOGD) << LOGD;                       // F * R doubles per lane and step
-    constexpr size_t stage = FR <= 16 ? (size_t)(FR <= 8 ? 4 : 2) * (FR / 2) * 32 * 16 : 0;   // cp.async ring (skb_fwd5.cuh)
+    constexpr size_t stage = FR <= 32 ? (size_t)(FR <= 8 ? 4 : (FR <= 16 ? 2 : 1)) * (FR / 2) * 32 * 16 : 0;   // cp.async ring (skb_fwd5.cuh)
     const size_t smem = MODE == MODE_REV_GRAD ? (size_t)RC * (a.D + 1) * 32 * sizeof(double) + stage : 0;
     fwd5_kernel<KIND, RC, LOGD, DP2, 1, MINB, UNR, MODE><<<(unsigned)nb, 32, smem, st>>>(a);
     return check_launch();
