@@ -79,6 +79,7 @@ int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, voi
 /* Which kernel family a call would use (host-side dispatch only, no GPU work; for tests and diagnostics):
  *   skb_forward_plan  (skb_sigkernel_fwd):      0 = generic row-band sweep of the fine grid (any shape),
  *                                               1 = register-resident solver_kernel (v4),
+ *                                               4 = fwd5_kernel with 16 lanes per pair (two pairs per warp),
  *                                               5 / 6 / 7 = fwd5_kernel with 1 / 2 / 4 warps per pair;
  *   skb_adjoint_plan  (skb_sigkernel_fwd_bwd): -4 (SKB_ERR_UNSUPPORTED) = shape not covered by the backward,
  *                                               1 = solver_kernel store / reversed modes (v4),

@@ -182,8 +182,9 @@ int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int
     if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
     if (fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1)) {
-        const int nw = fwd5_warps_per_pair(M, dyadic_order);
-        return nw == 1 ? 5 : (nw == 2 ? 6 : 7);
+        int lpp = 32;
+        const int nw = fwd5_warps_per_pair(M, dyadic_order, &lpp);
+        return lpp == 16 ? 4 : (nw == 1 ? 5 : (nw == 2 ? 6 : 7));
     }
     return solver_rows_per_lane(M, dyadic_order) >= 0 ? 1 : 0;
 }

@@ -205,9 +205,30 @@ static bool fwd5_shape_ok(int rc, int logd) {   // SKB_FWD5_SHAPES of skb_fwd5.c
     return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 2) || (rc == 4 && logd == 0);
 }
 
+static bool fwd5_l16_shape_ok(int rc, int logd) {   // SKB_FWD5_L16_SHAPES of skb_fwd5.cuh
+    return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 3) || (rc == 4 && logd <= 2);
+}
+
 // warps per pair fwd5 would use (1, 2 or 4: the smallest count whose per-lane strip is an instantiated
-// shape), and the coarse rows per lane that go with it; 0 if the shape is not covered
-static int fwd5_plan(int M, int logd, int* rc_out) {
+// shape), the coarse rows per lane and the lanes per pair that go with it; 0 if the shape is not covered.
+// Short paths (len_x <= 64) take the 16-lanes-per-pair variant when its strip is instantiated: twice the
+// cells per lane and step for the same per-step overhead (measured 0.41 -> 0.35 ms at the headline config).
+static int fwd5_plan(int M, int logd, int* rc_out, int* lpp_out = nullptr) {
+    static int l16 = -1;
+    if (l16 < 0) {
+        const char* e = getenv("SKB_LPP16");      // development switch: SKB_LPP16=0 disables the 16-lane variant
+        l16 = e ? atoi(e) : 1;
+    }
+    if (lpp_out) *lpp_out = 32;
+    if (l16) {
+        int rc = (M + 15) / 16, rcp = 1;
+        while (rcp < rc) rcp <<= 1;
+        if (fwd5_l16_shape_ok(rcp, logd)) {
+            if (rc_out) *rc_out = rcp;
+            if (lpp_out) *lpp_out = 16;
+            return 1;
+        }
+    }
     for (int nw = 1; nw <= 4; nw *= 2) {
         int rc = (M + 32 * nw - 1) / (32 * nw), rcp = 1;
         while (rcp < rc) rcp <<= 1;
@@ -219,7 +240,7 @@ static int fwd5_plan(int M, int logd, int* rc_out) {
     return 0;
 }
 
-int fwd5_warps_per_pair(int M, int logd) { return fwd5_plan(M, logd, nullptr); }
+int fwd5_warps_per_pair(int M, int logd, int* lpp) { return fwd5_plan(M, logd, nullptr, lpp); }
 
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     if (!use_fwd5() || s1 || N < 4) return false;
@@ -271,8 +292,8 @@ int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
 }
 
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
-    int rcp = 0;
-    const int nw = fwd5_plan(args.M, logd, &rcp);
+    int rcp = 0, lpp = 32;
+    const int nw = fwd5_plan(args.M, logd, &rcp, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
     fill_v5_constants(args, logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
@@ -283,7 +304,11 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
     static const fwd5_fn table[2][3] = {
         {launch_group_fwd5_lin_nw1, launch_group_fwd5_lin_nw2, launch_group_fwd5_lin_nw4},
         {launch_group_fwd5_rbf_nw1, launch_group_fwd5_rbf_nw2, launch_group_fwd5_rbf_nw4}};
-    rc = table[kind == KIND_RBF ? 1 : 0][nw == 1 ? 0 : (nw == 2 ? 1 : 2)](rcp, logd, args.Dp / 2, args, st);
+    if (lpp == 16)
+        rc = kind == KIND_RBF ? launch_group_fwd5_rbf_l16(rcp, logd, args.Dp / 2, args, st)
+                              : launch_group_fwd5_lin_l16(rcp, logd, args.Dp / 2, args, st);
+    else
+        rc = table[kind == KIND_RBF ? 1 : 0][nw == 1 ? 0 : (nw == 2 ? 1 : 2)](rcp, logd, args.Dp / 2, args, st);
     if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return rc;
 }

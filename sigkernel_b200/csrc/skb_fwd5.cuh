@@ -34,6 +34,10 @@ namespace skb {
 // warps per SM); larger strips stay with solver_kernel.  Keep in sync with fwd5_shape_ok() (skb_dispatch.cu).
 #define SKB_FWD5_SHAPES(X) X(1, 0) X(1, 1) X(1, 2) X(1, 3) X(2, 0) X(2, 1) X(2, 2) X(4, 0)
 
+// (RC, LOGD) shapes of the 16-lanes-per-pair variant (len_x <= 16 RC): strips of at most 16 fine rows.
+// Keep in sync with fwd5_l16_shape_ok() (skb_dispatch.cu).
+#define SKB_FWD5_L16_SHAPES(X) X(1, 0) X(1, 1) X(1, 2) X(1, 3) X(2, 0) X(2, 1) X(2, 2) X(2, 3) X(4, 0) X(4, 1) X(4, 2)
+
 // shapes of the adjoint modes: one warp per pair, dyadic order >= 1 (MM and the strips even: 16-byte grid rows).
 // Keep in sync with adjoint5_shape_ok() (skb_dispatch.cu).
 #define SKB_ADJ5_SHAPES(X) X(1, 1) X(1, 2) X(1, 3) X(2, 1) X(2, 2)
@@ -108,8 +112,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //                   sigkernel.py:438-469), multiplied cell by cell with the stored forward grid (read one step
 //                   ahead), reduced to coarse sensitivities S and contracted with the analytic static-kernel
 //                   derivative into per-point gradients (sigkernel.py:470-500), see solver_kernel
-template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0>
+// LPP = lanes per pair: 32 (default), or 16 -- then a warp carries TWO independent pair streams (lanes 0-15 and
+// 16-31), each lane owns twice the rows and the per-step overhead is spread over twice the cells.
+template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0, int LPP = 32>
 __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
+    static_assert(LPP == 32 || (LPP == 16 && NW == 1 && MODE == 0), "16 lanes per pair: forward only, one warp");
+    constexpr int NSTR = 32 / LPP;               // pair streams per warp
     constexpr int F = 1 << LOGD;
     constexpr int R = RC * F;
     constexpr bool STORE = MODE == MODE_FWD_STORE, REVG = MODE == MODE_REV_GRAD;
@@ -124,18 +132,23 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int NP = F * R / 2;                // 16-byte pieces per lane and step
     constexpr bool GREG = REVG && (RC * DP2 <= 6);   // gradient accumulators in registers instead of shared memory
     constexpr int Dp = 2 * DP2;
-    constexpr bool XREG = (RC * DP2 <= 8);      // x rows of the pair in registers
+    constexpr bool XREG = (RC * DP2 <= ((LPP == 16 && R > 8) ? 12 : 8));   // x rows of the pair in registers (the 16-row
+                                                                           // strips run 8 warps per SM: room for 12 double2)
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
     constexpr int RING = 64;                     // job ring depth (lane 0 is < 32 NW steps = RING/2 wraps ahead)
     const int glane = threadIdx.x;               // position in the wavefront
     const int lane = glane & 31;
     const int wid = glane >> 5;
+    const int pl = LPP == 32 ? glane : (lane & (LPP - 1));   // position in the pair's wavefront
+    const int sid = LPP == 32 ? 0 : lane / LPP;               // pair stream of this lane
+    const int slot = LPP == 32 ? glane : sid * (LPP + 1) + pl;   // exchange slot (one boundary slot per stream)
     const int N = p.N, M = p.M;                  // N >= LEAD (the dispatcher sends shorter paths elsewhere)
-    const int G = gridDim.x;
-    const int first_job = blockIdx.x;
+    const int G = gridDim.x * NSTR;
+    const int first_job = blockIdx.x * NSTR + sid;
+    const bool has_job = first_job < p.njobs;
 
     __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
-    __shared__ int4 ring_s[RING];                // job stream: (job, x offset, y offset, -) in doubles
+    __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset, -) in bytes
     // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
     // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
     // slot g+1 and reads the row above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // first node row goes UP one lane.
     static_assert(UNR == 3, "the exchange buffers and the d history rotate with period 3");
     constexpr int H = (F + 1) / 2;
-    constexpr int NL = 32 * NW;
+    constexpr int NL = LPP == 32 ? 32 * NW : NSTR * (LPP + 1) - 1;   // exchange slots - 1
     constexpr int TXH = (NL + 1) * 16, TXQ = H * TXH;     // byte strides of tx[q][h][slot]
     constexpr int DXQ = (NL + 1) * 8;                       // byte stride of dx[q][slot]
     __shared__ double2 tx[3][H][NL + 1];
@@ -163,38 +176,38 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     unsigned xo, yo;                              // byte offsets of the production pair's paths
     {
         int a, b;
-        job_decode(p, p.job0 + first_job, a, b);
+        job_decode(p, p.job0 + (has_job ? first_job : 0), a, b);
         xo = (unsigned)a * xstride;
         yo = (unsigned)b * ystride;
-        if (glane == 0) {
+        if (pl == 0) {
             for (int q = 0; q < 3; ++q) {
-                for (int h = 0; h < H; ++h) tx[q][h][0] = make_double2(1.0, 1.0);
-                dx[q][NL] = 0.0;
+                for (int h = 0; h < H; ++h) tx[q][h][slot] = make_double2(1.0, 1.0);
+                dx[q][slot + LPP * (LPP == 32 ? NW : 1)] = 0.0;
             }
-            ring_s[0] = make_int4(first_job, (int)xo, (int)yo, 0);
-            job_next = (int)(G + atomicAdd(p.counter, 1u));
+            ring_s[sid][0] = make_int4(has_job ? first_job : -1, (int)xo, (int)yo, 0);
+            job_next = has_job ? (int)(G + atomicAdd(p.counter, 1u)) : p.njobs;
         }
     }
     if (NW > 1) __syncthreads(); else __syncwarp();
-    int c = (-glane - LEAD) % N;                  // stencil column; production column e = (c + LEAD) mod N
+    int c = (-pl - LEAD) % N;                     // stencil column; production column e = (c + LEAD) mod N
     if (c < 0) c += N;
-    int w = glane == 0 ? 0 : -((glane - 1) / N + 1);   // index of the pair the production stream is in (< 0: virtual)
-    int pjob = glane == 0 ? first_job : -1;       // production stream's job (-1: virtual or past the end)
+    int w = pl == 0 ? 0 : -((pl - 1) / N + 1);    // index of the pair the production stream is in (< 0: virtual)
+    int pjob = (pl == 0 && has_job) ? first_job : -1;   // production stream's job (-1: virtual or past the end)
     int sjob = -1;                                // stencil stream's job (-1: nothing to output)
-    bool done = false;
+    bool done = pl == 0 && !has_job;
     const int pc = (2 * N - 1 - LEAD) % N;        // stencil column at which the production column wraps
     // this lane holds grid row MM-1 (the output) in u[(orc + 1) * F - 1] iff 0 <= orc < RC
-    const int orc = (M - 2) - glane * RC;
+    const int orc = (M - 2) - pl * RC;
 
     const char* xrow0[RC];                        // this lane's node rows in X_0 (clamped rows never reach a valid cell)
 #pragma unroll
     for (int rc = 0; rc < RC; ++rc) {
-        int row = glane * RC + rc;
+        int row = pl * RC + rc;
         row = row < M ? row : M - 1;
         xrow0[rc] = reinterpret_cast<const char*>(p.Xp) + (size_t)row * (Dp * 8);
     }
-    const unsigned txb = (unsigned)__cvta_generic_to_shared(&tx[0][0][glane]);   // read slot; write slot = +16
-    const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][glane]);      // write slot; read slot = +8
+    const unsigned txb = (unsigned)__cvta_generic_to_shared(&tx[0][0][slot]);   // read slot; write slot = +16
+    const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][slot]);      // write slot; read slot = +8
 
     double2 xr[XREG ? RC : 1][DP2];
     const double* xrow[XREG ? 1 : RC];            // !XREG: the rows are re-read every step
@@ -592,7 +605,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 // the production column wraps: next pair
                 ++w;
                 int4 ent = make_int4(-1, (int)xo, (int)yo, 0);
-                if (glane == 0) {
+                if (pl == 0) {
                     int job = job_next;
                     if (job < p.njobs) {
                         job_next = (int)(G + atomicAdd(p.counter, 1u));
@@ -604,9 +617,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         job = -1;
                     }
                     ent.x = job;
-                    ring_s[w & (RING - 1)] = ent;
+                    ring_s[sid][w & (RING - 1)] = ent;
                 } else if (w >= 0) {
-                    ent = ring_s[w & (RING - 1)];     // written >= 1 step (= 1 barrier) ago
+                    ent = ring_s[sid][w & (RING - 1)];     // written >= 1 step (= 1 barrier) ago
                 }
                 pjob = ent.x;
                 if (w >= 0 && ent.x < 0) done = true;

@@ -86,10 +86,12 @@ int launch_group_fwd5_rbf_nw4(int rc, int logd, int dp2, const KArgs&, cudaStrea
 int launch_group_fwd5_lin_nw1(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_fwd5_lin_nw2(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_fwd5_lin_nw4(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_rbf_l16(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+int launch_group_fwd5_lin_l16(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 // true if skb_sigkernel_fwd should take the fwd5 path for this problem (scheme S2, N >= 4, shape instantiated)
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1);
-// warps per pair fwd5 would use (0: not covered)
-int fwd5_warps_per_pair(int M, int logd);
+// warps per pair fwd5 would use (0: not covered); *lpp (if given) receives the lanes per pair (32 or 16)
+int fwd5_warps_per_pair(int M, int logd, int* lpp = nullptr);
 // scale the static kernel is produced with on the fwd5 path (Linear: folded into the prepared X rows)
 double fwd5_kscale(int logd);
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st);
