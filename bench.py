@@ -306,7 +306,7 @@ def run_ours(args):
         roofline = {
             "bound": "fp64", "achieved": achieved / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
             "frac": achieved / peak_rate, "traffic": traffic,
-            "kernel": "fwd5_kernel<RBF,RC=2,LOGD=2,DP2=3,NW=1>", "kernel_ms": k_ms,
+            "kernel": "fwd5_kernel<RBF,RC=4,LOGD=2,DP2=3,NW=1,LPP=16>", "kernel_ms": k_ms,
             "peak_source": "measured live: register-resident DADD/DMUL chain (skb_fp64_probe); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "peak_dfma": peak["dfma"] / 1e12,
