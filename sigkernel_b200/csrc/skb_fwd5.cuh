@@ -1,29 +1,32 @@
-// skb_fwd5.cuh -- the forward-only kernel of the fused static kinds (Linear / RBF): the hot path of
-// compute_Gram / compute_kernel without gradients (BASELINE configs 2, 3, 5).
+// skb_fwd5.cuh -- the v5 kernel of the fused static kinds (Linear / RBF): the hot path of compute_Gram /
+// compute_kernel (MODE 0, every BASELINE config) and of the adjoint pass behind compute_mmd(...).backward()
+// (MODE_FWD_STORE / MODE_REV_GRAD).  DESIGN.md 3a / 4a have the measurements behind every choice below.
 //
-// Same decomposition as solver_kernel (skb_solver.cuh): one warp streams through path pairs, lane t owns
-// RC coarse rows (R = RC * 2^d fine rows in registers) and runs one macro step (= one coarse column)
-// behind lane t-1.  What is different -- every item below removes instructions, register-file reads or
-// exposed latency from the macro step, the three things the ncu source page of the v4 kernel showed it
-// to be bound by (profiles/r01_fwd_cfg3_*.json):
-//   * jobs are assigned statically (job = block + k * grid): every lane advances its own (a, b) with two
-//     adds and a carry when it wraps; no atomic queue, no per-step shuffles of the pair ids;
-//   * the lane's x rows live in registers for the whole pair (when RC * Dp <= 16 doubles) and the y row
-//     of the NEXT production column is loaded one macro step ahead: no load is consumed in the step
-//     that issued it (v4: 14 % of all stall samples were the first DADD after the loads);
-//   * the static kernel is kept as COLUMN DIFFERENCES d[i][j] = k[i][j+1] - k[i][j]; the increment of a
-//     coarse cell is g = d[i+1][j] - d[i][j], so one value (not two) comes from lane t+1 and a coarse cell
-//     costs 5 DP instructions instead of 8 (the dyadic scale 4^-d is folded into the polynomial
-//     coefficients c1 = 4^-d / 2, c2 = 16^-d / 12, constant-bank operands);
-//   * every shuffle is issued by the PRODUCER as soon as its source exists (the bottom-row value of fine
-//     column f right after its cell, the d history one step early), so a full macro step of independent
-//     work covers the SHFL latency instead of the first cells of the next step waiting on it;
-//   * production runs 4 columns ahead of the stencil (v4: 3) so that the shuffled d value is one step old;
-//   * the exp() underflow guard is one integer min on the high word instead of DSETP + 4 FSEL.
+// Same decomposition as solver_kernel (skb_solver.cuh): a warp streams through path pairs, lane t owns RC coarse
+// rows (R = RC * 2^d fine rows in registers) and runs one macro step (= one coarse column) behind lane t-1.
+// What is different:
+//   * lane 0 pops an atomic job queue one pair ahead and publishes (job, byte offsets of X_a, Y_b) in a ring in
+//     shared memory; lane t picks its entry up when its own production column wraps: no per-step shuffles of the
+//     pair ids, and warps that drift apart are rebalanced (a static assignment lost 24 % to the tail);
+//   * the lane's x rows live in registers for the whole pair (when they fit) and the y row of the NEXT
+//     production column is loaded one macro step ahead: no load is consumed in the step that issued it;
+//   * the static kernel is kept as COLUMN DIFFERENCES d[i][j] = k[i][j+1] - k[i][j], produced pre-scaled by
+//     4^-d / sqrt(12); the increment of a coarse cell is one subtraction, its coefficients three more DP
+//     instructions, and ONE value (not two) goes up a lane;
+//   * the two neighbour exchanges (bottom row down, d of the first row up) go through triple-buffered shared-
+//     memory slots written by the PRODUCER as soon as the value exists and read after one warp / block barrier;
+//     slot 0 is the boundary u = 1 (no lane-0 select) and a warp boundary is just another slot, which is how
+//     2 or 4 warps share one long pair (NW) and how 16 lanes suffice for a short one (LPP = 16: two pair streams
+//     per warp, twice the cells per lane and step for the same per-step overhead);
+//   * production runs 4 columns ahead of the stencil so that the exchanged d value is one step old;
+//   * the three per-pair events (output, boundary re-arm, production wrap) hang off one test per step;
+//   * the exp() underflow guard is one unsigned min on the high word; constants are constant-bank operands;
+//   * adjoint modes: lane-major stored grid, 256-bit sector stores / loads, the reversed sweep reads its rows
+//     through a per-lane cp.async ring 4 steps ahead, gradient accumulators in registers.
 //
-// fp64 throughout, FMA arithmetic (u11 = a (u10 + u01) + (-b) u00), results within 1e-13 of v4.
-// Reference semantics replaced: sigkernel/cuda_backend.py:121-160 (+ :6-49), static_kernels.py:17-33,
-// 42-73, sigkernel.py:362-364, 607-613 -- see skb_solver.cuh for the mapping.
+// fp64 throughout, FMA arithmetic (u11 = a (u10 + u01) + (-b) u00), results within 1e-13 of solver_kernel.
+// Reference semantics replaced: sigkernel/cuda_backend.py:121-160 (+ :6-49), static_kernels.py:17-33, 42-73,
+// sigkernel.py:362-364, 607-613 (forward) and :419-502, 256-343 (adjoint) -- see skb_solver.cuh for the mapping.
 #pragma once
 #include <type_traits>
 #include "skb_solver.cuh"
