@@ -339,3 +339,22 @@ def test_fwd5_long_stream_single_block(skb, O):
     finally:
         lib.skb_set_warps_per_sm(0)
     assert fwd_err(out.view(30, 50).cpu().numpy(), ref.numpy()) <= FWD_TOL
+
+
+def test_overflowing_pair_does_not_leak_into_its_stream(skb, O):
+    """A pair whose PDE solution overflows fp64 returns inf / NaN (as the reference does) and the pairs that follow
+    it in the same warp stream are unaffected: every per-pair state is re-armed by assignment, not arithmetic."""
+    X = make_paths("bm", 61, (5, 20, 3))
+    Y = make_paths("bm", 62, (30, 18, 3))
+    X[2] *= 1e90                                   # increments ~1e90: the grid of every pair (2, b) overflows
+    ref = O.compute_Gram(X, Y, O.LinearKernel(), 2).numpy()
+    bad = ~np.isfinite(ref)
+    assert bad[2].all() and not bad[[0, 1, 3, 4]].any()
+    for wpsm in (0, 1):                            # 1: few streams, every one of them runs through overflowed pairs
+        skb._lib.lib.skb_set_warps_per_sm(wpsm)
+        try:
+            got = skb.SigKernel(skb.LinearKernel(), 2).compute_Gram(X.cuda(), Y.cuda()).cpu().numpy()
+        finally:
+            skb._lib.lib.skb_set_warps_per_sm(0)
+        assert (~np.isfinite(got[2])).all()
+        assert fwd_err(got[~bad], ref[~bad]) <= FWD_TOL
