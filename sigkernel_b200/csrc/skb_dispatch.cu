@@ -205,6 +205,10 @@ static bool fwd5_shape_ok(int rc, int logd) {   // SKB_FWD5_SHAPES of skb_fwd5.c
     return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 2) || (rc == 4 && logd == 0);
 }
 
+static bool fwd5_r16_shape_ok(int rc, int logd) {   // SKB_FWD5_R16_SHAPES: one warp per pair only
+    return (rc == 2 && logd == 3) || (rc == 4 && logd == 2) || (rc == 8 && logd == 1);
+}
+
 static bool fwd5_l16_shape_ok(int rc, int logd) {   // SKB_FWD5_L16_SHAPES of skb_fwd5.cuh
     return (rc == 1 && logd <= 3) || (rc == 2 && logd <= 3) || (rc == 4 && logd <= 2);
 }
@@ -232,7 +236,7 @@ static int fwd5_plan(int M, int logd, int* rc_out, int* lpp_out = nullptr) {
     for (int nw = 1; nw <= 4; nw *= 2) {
         int rc = (M + 32 * nw - 1) / (32 * nw), rcp = 1;
         while (rcp < rc) rcp <<= 1;
-        if (fwd5_shape_ok(rcp, logd)) {
+        if (fwd5_shape_ok(rcp, logd) || (nw == 1 && fwd5_r16_shape_ok(rcp, logd))) {
             if (rc_out) *rc_out = rcp;
             return nw;
         }

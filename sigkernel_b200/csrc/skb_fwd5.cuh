@@ -36,6 +36,9 @@ namespace skb {
 // (RC, LOGD) shapes fwd5 is instantiated for: the strips that fit 128 registers without spilling (16 resident
 // warps per SM); larger strips stay with solver_kernel.  Keep in sync with fwd5_shape_ok() (skb_dispatch.cu).
 #define SKB_FWD5_SHAPES(X) X(1, 0) X(1, 1) X(1, 2) X(1, 3) X(2, 0) X(2, 1) X(2, 2) X(4, 0)
+// 16-row strips, one warp per pair only (8 resident warps per SM): len_x <= 128 at dyadic order 2 runs faster this
+// way than with two warps and a block barrier per step (3.33 vs 3.67 ms on one rank's share of cfg5)
+#define SKB_FWD5_R16_SHAPES(X) X(2, 3) X(4, 2) X(8, 1)
 
 // (RC, LOGD) shapes of the 16-lanes-per-pair variant (len_x <= 16 RC): strips of at most 16 fine rows.
 // Keep in sync with fwd5_l16_shape_ok() (skb_dispatch.cu).
@@ -213,19 +216,24 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][slot]);      // write slot; read slot = +8
 
     double2 xr[XREG ? RC : 1][DP2];
-    const double* xrow[XREG ? 1 : RC];            // !XREG: the rows are re-read every step
+    // !XREG: the lane's rows are staged in shared memory once per pair ([piece][lane]: conflict-free 16-byte
+    // accesses) and re-read every step from there -- global loads consumed in the step that issues them were the
+    // reason the wide-row shapes (D + 1 = 10) ran latency-bound
+    constexpr bool XSM = !XREG && (RC * DP2 * 32 * NW * 16 <= 20480);   // (else: straight from global / L1 every step)
+    __shared__ double2 xs_s[XSM ? RC * DP2 : 1][XSM ? 32 * NW : 1];
+    const double* xrow[(XREG || XSM) ? 1 : RC];
     const double* yp = p.Yp;                      // y row of the NEXT production column
     auto set_pair = [&]() {
         yp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + yo);
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) {
             const double* xp = reinterpret_cast<const double*>(xrow0[rc] + xo);
-            if (XREG) {
 #pragma unroll
-                for (int i = 0; i < DP2; ++i) xr[rc][i] = ldg2(xp + 2 * i);
-            } else {
-                xrow[XREG ? 0 : rc] = xp;
+            for (int i = 0; i < DP2; ++i) {
+                if (XREG) xr[XREG ? rc : 0][i] = ldg2(xp + 2 * i);
+                else if (XSM) xs_s[XSM ? rc * DP2 + i : 0][XSM ? glane : 0] = ldg2(xp + 2 * i);
             }
+            if (!XREG && !XSM) xrow[(XREG || XSM) ? 0 : rc] = xp;
         }
     };
     set_pair();
@@ -518,11 +526,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         double dnew[RC];
 #pragma unroll
         for (int rc = 0; rc < RC; ++rc) {
-            double2 xv = XREG ? xr[XREG ? rc : 0][0] : ldg2(xrow[XREG ? 0 : rc]);
+            double2 xv = XREG ? xr[XREG ? rc : 0][0] : (XSM ? xs_s[XSM ? rc * DP2 : 0][XSM ? glane : 0] : ldg2(xrow[(XREG || XSM) ? 0 : rc]));
             double acc = fma(xv.y, yq[0].y, xv.x + yq[0].x);
 #pragma unroll
             for (int i = 1; i < DP2; ++i) {
-                xv = XREG ? xr[XREG ? rc : 0][i] : ldg2(xrow[XREG ? 0 : rc] + 2 * i);
+                xv = XREG ? xr[XREG ? rc : 0][i] : (XSM ? xs_s[XSM ? rc * DP2 + i : 0][XSM ? glane : 0] : ldg2(xrow[(XREG || XSM) ? 0 : rc] + 2 * i));
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
             if (KIND == KIND_RBF) acc = exp_neg5(acc, etab, p);

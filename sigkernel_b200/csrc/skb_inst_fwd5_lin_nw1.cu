@@ -5,7 +5,7 @@ namespace skb {
 
 template <int KIND, int RC, int LOGD, int DP2, int NW>
 static int launch_fwd5(const KArgs& a, cudaStream_t st) {
-    constexpr int MINB = 16 / NW, UNR = 3;       // 16 resident warps per SM
+    constexpr int MINB = ((RC << LOGD) > 8 ? 8 : 16) / NW, UNR = 3;       // 16 resident warps per SM (8 with 16-row strips)
     int bpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() / NW : MINB;
     if (bpsm > MINB) bpsm = MINB;
     if (bpsm < 1) bpsm = 1;
@@ -27,6 +27,7 @@ static int launch_nw(int rc, int logd, int dp2, const KArgs& a, cudaStream_t st)
         }                                                                               \
     }
     SKB_FWD5_SHAPES(SKB_CASE)
+    SKB_FWD5_R16_SHAPES(SKB_CASE)       // this translation unit is NW = 1
 #undef SKB_CASE
     return SKB_ERR_UNSUPPORTED;
 }

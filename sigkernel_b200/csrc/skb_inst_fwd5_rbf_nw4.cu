@@ -5,7 +5,7 @@ namespace skb {
 
 template <int KIND, int RC, int LOGD, int DP2, int NW>
 static int launch_fwd5(const KArgs& a, cudaStream_t st) {
-    constexpr int MINB = 16 / NW, UNR = 3;       // 16 resident warps per SM
+    constexpr int MINB = ((RC << LOGD) > 8 ? 8 : 16) / NW, UNR = 3;       // 16 resident warps per SM (8 with 16-row strips)
     int bpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() / NW : MINB;
     if (bpsm > MINB) bpsm = MINB;
     if (bpsm < 1) bpsm = 1;

@@ -164,9 +164,10 @@ def test_dispatch_plans_for_the_baseline_configs():
     assert lib.skb_forward_plan(32, 32, 3, 1, RBF, S2) == 4      # cfg2
     assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S2) == 4      # cfg3 (headline)
     assert lib.skb_forward_plan(64, 64, 3, 1, RBF, S2) == 4      # cfg4 forward
-    assert lib.skb_forward_plan(64, 64, 5, 3, RBF, S2) == 6      # 32-row strips are not instantiated: 2 warps x 8 rows
+    assert lib.skb_forward_plan(64, 64, 5, 3, RBF, S2) == 5      # dyadic order 3: one warp, 16-row strips
+    assert lib.skb_forward_plan(200, 9, 3, 2, RBF, S2) == 7      # len_x = 200 at dyadic order 2: four warps per pair
     assert lib.skb_forward_plan(100, 11, 8, 1, RBF, S2) == 6     # len_x > 64: 32 lanes per pair, 2 warps
-    assert lib.skb_forward_plan(128, 128, 8, 2, RBF, S2) == 6    # cfg5: two warps per pair
+    assert lib.skb_forward_plan(128, 128, 8, 2, RBF, S2) == 5    # cfg5: one warp per pair, 16-row strips
     assert lib.skb_forward_plan(250, 9, 3, 2, RBF, S2) == 7      # four warps per pair
     assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S1) == 1      # _naive_solver: v4 kernel
     assert lib.skb_forward_plan(64, 3, 5, 2, RBF, S2) == 1       # len_y < 4: v4 kernel
