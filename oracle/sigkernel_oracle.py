@@ -180,6 +180,70 @@ class RBFKernel:
         return torch.exp(-dist / self.sigma)
 
 
+# function-space kernels (static_kernels.py:75-250): paths are (batch, len_t, len_x, dim); every one of them
+# is a path transform in front of Linear / RBF
+def cos_exp_kernel(x_y, n_freqs=5, sigma=1):
+    """static_kernels.py:233-250."""
+    cos_term = torch.cos(2 * torch.pi * x_y[:, :, None] * torch.arange(n_freqs)[None, None]).sum(dim=-1)
+    return cos_term * torch.exp(-x_y ** 2 / sigma)
+
+
+def CEXP(X, n_freqs=20, sigma=np.sqrt(10)):
+    """static_kernels.py:208-231: integral operator of the cos-exp kernel along the len_x axis."""
+    length_x = X.shape[2]
+    grid = torch.linspace(0, 1, length_x, dtype=torch.float64)
+    T_mat = cos_exp_kernel(grid[:, None] - grid[None, :], n_freqs=n_freqs, sigma=sigma)
+    return ((1. / length_x) * torch.matmul(X.permute(0, 1, 3, 2), T_mat)).permute(0, 1, 3, 2)
+
+
+def _flat(X):
+    return X.reshape(X.shape[0], X.shape[1], -1)
+
+
+class Linear_ID_Kernel(LinearKernel):
+    """static_kernels.py:146-175."""
+
+    def transform(self, X):
+        return _flat(X)
+
+    def batch_kernel(self, X, Y):
+        return super().batch_kernel(_flat(X), _flat(Y))
+
+    def Gram_matrix(self, X, Y):
+        return super().Gram_matrix(_flat(X), _flat(Y))
+
+
+class RBF_ID_Kernel(RBFKernel):
+    """static_kernels.py:178-206."""
+
+    def transform(self, X):
+        return _flat(X)
+
+    def batch_kernel(self, X, Y):
+        return super().batch_kernel(_flat(X), _flat(Y))
+
+    def Gram_matrix(self, X, Y):
+        return super().Gram_matrix(_flat(X), _flat(Y))
+
+
+class RBF_CEXP_Kernel(RBFKernel):
+    """static_kernels.py:75-115."""
+
+    def __init__(self, sigma1, sigma2, n_freqs):
+        self.sigma1 = sigma1
+        super().__init__(sigma2)
+        self.n_freqs = n_freqs
+
+    def transform(self, X):
+        return _flat(CEXP(X, self.n_freqs, self.sigma1))
+
+    def batch_kernel(self, X, Y):
+        return super().batch_kernel(self.transform(X), self.transform(Y))
+
+    def Gram_matrix(self, X, Y):
+        return super().Gram_matrix(self.transform(X), self.transform(Y))
+
+
 # ---------------------------------------------------------------------------------------
 # increments: second difference + dyadic refinement (sigkernel.py:217-218, 362-364, 607-613)
 # ---------------------------------------------------------------------------------------

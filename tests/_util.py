@@ -60,3 +60,19 @@ def make_paths(kind, seed, shape, dtype=torch.float64):
     if kind == "bm":
         return torch.cumsum(torch.randn(shape, dtype=dtype, generator=g) / np.sqrt(shape[1]), 1)
     raise ValueError(kind)
+
+
+def static_of(mod, meta):
+    """Static kernel object of module `mod` (the oracle or sigkernel_b200) for a golden fixture's metadata."""
+    kind = meta["static"]
+    if kind == "rbf":
+        return mod.RBFKernel(meta["param"])
+    if kind == "linear":
+        return mod.LinearKernel(meta["param"])
+    if kind == "rbf_id":
+        return mod.RBF_ID_Kernel(meta["params"][0])
+    if kind == "linear_id":
+        return mod.Linear_ID_Kernel()
+    if kind == "rbf_cexp":
+        return mod.RBF_CEXP_Kernel(*meta["params"])
+    raise ValueError(kind)

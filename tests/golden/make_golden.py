@@ -34,6 +34,12 @@ import sigkernel as ref  # noqa: E402  (the unmodified reference)
 def make_kernel(spec):
     if spec[0] == "rbf":
         return ref.RBFKernel(sigma=spec[1])
+    if spec[0] == "rbf_id":          # function-space kernels (static_kernels.py:75-206): 4-D inputs
+        return ref.RBF_ID_Kernel(spec[1])
+    if spec[0] == "linear_id":
+        return ref.Linear_ID_Kernel()
+    if spec[0] == "rbf_cexp":
+        return ref.RBF_CEXP_Kernel(spec[1], spec[2], spec[3])
     return ref.LinearKernel(scale=spec[1])
 
 
@@ -84,6 +90,19 @@ CASES = [
     ("mmd_bwd_small", "mmd_bwd", ("rbf", 0.5), 1, False, "rand", 20, (5, 8, 3), (4, 8, 3), {}),
     ("scoring_rule", "scoring", ("rbf", 1.0), 1, False, "randn", 21, (5, 7, 2), (1, 7, 2), {}),
     ("distance", "distance", ("rbf", 1.0), 0, False, "randn", 22, (4, 7, 2), (4, 7, 2), {}),
+    # function-space static kernels (static_kernels.py:75-206): paths are (batch, len_t, len_x, dim)
+    ("fs_gram_rbf_id", "gram", ("rbf_id", 2.0), 1, False, "rand", 40, (3, 9, 4, 2), (4, 7, 4, 2), {}),
+    ("fs_kernel_rbf_id", "kernel", ("rbf_id", 1.5), 0, False, "rand", 41, (3, 8, 3, 1), (3, 6, 3, 1), {}),
+    ("fs_gram_linear_id", "gram", ("linear_id",), 2, False, "bm", 42, (3, 6, 2, 2), (2, 9, 2, 2), {}),
+    ("fs_gram_rbf_cexp", "gram", ("rbf_cexp", 1.0, 2.0, 4), 1, False, "rand", 43, (3, 7, 4, 2), (3, 7, 4, 2), {}),
+    ("fs_gram_rbf_id_wide", "gram", ("rbf_id", 8.0), 1, False, "rand", 44, (2, 6, 8, 2), (3, 6, 8, 2), {}),
+    # (the reference's backward does not support 4-D inputs: prep_backward permutes a 5-D tensor with 4 indices,
+    #  sigkernel.py:476 -> RuntimeError; forward only)
+    # adjoint pass beyond 256 points per path (the reference's GPU limit is (len-1) * 2^d < 1024)
+    ("gram_bwd_len300_d1", "gram_bwd", ("rbf", 1.0), 1, False, "bm", 50, (2, 300, 2), (2, 40, 2), {}),
+    ("gram_bwd_len600_d0", "gram_bwd", ("rbf", 1.0), 0, False, "bm", 51, (2, 600, 3), (2, 33, 3), {}),
+    ("gram_bwd_len1000_d0", "gram_bwd", ("linear", 1.0), 0, False, "bm", 52, (1, 1000, 2), (2, 25, 2), {}),
+    ("kernel_bwd_rbf_d0", "kernel_bwd", ("rbf", 0.7), 0, False, "rand", 53, (4, 12, 3), (4, 9, 3), {}),
 ]
 
 
@@ -130,8 +149,8 @@ def run_case(case):
         out["mmd"], out["grad"] = m.detach().numpy(), Xg.grad.numpy()
     else:
         raise ValueError(op)
-    meta = dict(name=name, op=op, static=kspec[0], param=kspec[1], dyadic_order=d, naive=naive,
-                data=kind, seed=seed)
+    meta = dict(name=name, op=op, static=kspec[0], param=(kspec[1] if len(kspec) > 1 else 1.0),
+                params=list(kspec[1:]), dyadic_order=d, naive=naive, data=kind, seed=seed)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), X=X.numpy(), Y=Y.numpy(),
                         meta=json.dumps(meta), **out)
     return meta
@@ -205,6 +224,9 @@ if __name__ == "__main__":
             m = run_deriv_case(c)
             print("wrote", m["name"], m["op"])
         sys.exit(0)
+    only = sys.argv[1:]
     for c in CASES:
+        if only and not any(c[0].startswith(o) for o in only):
+            continue
         m = run_case(c)
         print("wrote", m["name"], m["op"])

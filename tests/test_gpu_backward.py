@@ -28,7 +28,7 @@ def O():
 
 
 def _static(mod, meta):
-    return mod.RBFKernel(meta["param"]) if meta["static"] == "rbf" else mod.LinearKernel(meta["param"])
+    return static_of(mod, meta)
 
 
 def _dev(a):

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests._util import FWD_TOL, fwd_err, golden_names, load_golden, make_paths
+from tests._util import FWD_TOL, fwd_err, golden_names, load_golden, make_paths, static_of
 
 pytestmark = pytest.mark.gpu
 
@@ -30,7 +30,7 @@ def O():
 
 
 def _static(mod, meta):
-    return mod.RBFKernel(meta["param"]) if meta["static"] == "rbf" else mod.LinearKernel(meta["param"])
+    return static_of(mod, meta)
 
 
 def _dev(a):
