@@ -6,7 +6,10 @@
  * plain pointers and sizes, no torch types.  Every pointer named "device" is a CUDA
  * device pointer to contiguous row-major memory owned by the CALLER; nothing is
  * allocated inside the library; every launch is asynchronous on the `stream` argument
- * (a cudaStream_t passed as void*; NULL = legacy default stream) and re-entrant.
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).  The compute entry points keep
+ * no state between calls and may be called from several threads at once; the only process-wide
+ * state is the three tuning / measurement knobs below (skb_set_warps_per_sm, skb_set_tile_mode:
+ * plain ints read at launch time; skb_set_profile_events: per calling thread).
  *
  * Notation: A, B batch sizes; M, N path lengths (points); D path dimension; d dyadic
  * order; MM = (M-1) << d, NN = (N-1) << d fine cells per axis.
@@ -65,8 +68,14 @@ int         skb_version(void);             /* ABI version, bumped on any signatu
 /* Tuning knob (process-wide, default 0 = automatic): resident solver warps per SM. */
 void skb_set_warps_per_sm(int warps);
 
-/* Measurement hook (process-wide): when both are non-NULL, every solver launch records `start`
- * immediately before and `stop` immediately after the solver kernel on the launch stream
+/* Tuning knob (process-wide, default -1): which forward kernel serves skb_sigkernel_fwd for the fused static
+ * kinds.  1 = the experimental tile kernel (one pair per lane, one strip per warp, skb_tile.cuh) whenever the shape
+ * is instantiated (dyadic order 1..3, len_y >= 16, GRAM / BATCH pairs); 0 or -1 = fwd5_kernel / solver_kernel
+ * (the tile kernel is slower than fwd5_kernel at every BASELINE config so far). */
+void skb_set_tile_mode(int mode);
+
+/* Measurement hook (per calling thread): when both are non-NULL, every solver launch made by this thread records
+ * `start` immediately before and `stop` immediately after the solver kernel on the launch stream
  * (cudaEvent_t passed as void*), so a caller can time the dominant kernel alone, without the
  * path-preparation kernels around it.  Pass NULLs to disable. */
 void skb_set_profile_events(void* start_event, void* stop_event);

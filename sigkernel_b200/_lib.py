@@ -24,6 +24,7 @@ SYMBOLS = {
     "skb_last_cuda_error": (_i, []),
     "skb_version": (_i, []),
     "skb_set_warps_per_sm": (None, [_i]),
+    "skb_set_tile_mode": (None, [_i]),
     "skb_set_profile_events": (None, [_vp, _vp]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "skb_forward_plan": (_i, [_i, _i, _i, _i, _i, _i]),

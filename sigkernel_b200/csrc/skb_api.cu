@@ -174,6 +174,7 @@ const char* skb_error_string(int code) {
 int skb_last_cuda_error(void) { return g_last_cuda; }
 int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
+void skb_set_tile_mode(int mode) { set_tile_mode(mode); }
 void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme) {
@@ -202,6 +203,9 @@ size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_ord
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return 0;
     const size_t Dp = (size_t)padded_dim(D);
     size_t w = kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double));
+    // (sized for either static kind and scheme: the tile path's part is added whenever the shape could take it)
+    if (tile_applies(KIND_RBF, A, B, M, N, D, dyadic_order, false, pairs))
+        w += tile_workspace_bytes(A, B, M, N, dyadic_order, pairs);
     if (solver_rows_per_lane(M, dyadic_order) < 0)
         w += generic_workspace_bytes(njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM), M, N, dyadic_order, true);
     return w;
@@ -252,10 +256,13 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
-    const bool use5 = fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
+    const bool use_tile = tile_applies(kind, A, B, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1, pairs) &&
+                          workspace_bytes >= fixed_bytes + tile_workspace_bytes(A, B, M, N, dyadic_order, pairs);
+    const bool use5 = !use_tile && fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
                       (size_t)A * M * padded_dim(D) * sizeof(double) < ((size_t)1 << 32) &&
                       (size_t)B * N * padded_dim(D) * sizeof(double) < ((size_t)1 << 32);   // 32-bit byte offsets in the job ring
-    if (use5 && kind == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on that path
+    if ((use5 || use_tile) && kind == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on those paths
+    if (((use5 && fwd5_scaled_exp(M, dyadic_order, D)) || use_tile) && kind == KIND_RBF) { cx *= tile_arg_scale(); nsc *= tile_arg_scale(); }   // exp argument in units of ln2 / 2048
     rc = launch_prep2(X, Y, io_dtype, Xp, nullptr, Yp, nullptr, A, M, B, N, D, Dp, cx, nsc, counter, st);
     if (rc) return rc;
 
@@ -266,6 +273,7 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
     a.Dp = Dp; a.D = D;
+    if (use_tile) return launch_tile_forward(kind, dyadic_order, a, w + fixed_bytes, st);
     if (use5) return launch_forward5(kind, dyadic_order, a, st);
     if (solver_rows_per_lane(M, dyadic_order) >= 0) return launch_solver(MODE_FWD, kind, dyadic_order, false, a, st);
     // shape outside the register-resident kernels: generic row-band fallback (a symmetric request is

@@ -1,8 +1,10 @@
 // skb_dispatch.cu -- path preparation kernel and the host-side dispatcher of solver_kernel.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "skb_common.cuh"
 #include "skb_host.h"
+#include "skb_tile.cuh"
 
 namespace skb {
 
@@ -148,7 +150,7 @@ int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, 
     return check_launch();
 }
 
-static cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 void set_profile_events(void* a, void* b) { g_ev_start = (cudaEvent_t)a; g_ev_stop = (cudaEvent_t)b; }
 
 static int g_warps_per_sm = 0;
@@ -189,14 +191,6 @@ int solver_rows_per_lane(int M, int logd) {
     return rcp << logd;
 }
 
-static bool use_fwd5() {
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("SKB_FWD5");      // development switch: SKB_FWD5=0 forces the v4 kernel
-        v = s ? atoi(s) : 1;
-    }
-    return v != 0;
-}
 
 // ---- fwd5: the forward-only kernel of the fused kinds (skb_fwd5.cuh) ---------------------------------
 double fwd5_kscale(int logd) { return scale4_of_logd(logd) / sqrt(12.0); }
@@ -218,13 +212,8 @@ static bool fwd5_l16_shape_ok(int rc, int logd) {   // SKB_FWD5_L16_SHAPES of sk
 // Short paths (len_x <= 64) take the 16-lanes-per-pair variant when its strip is instantiated: twice the
 // cells per lane and step for the same per-step overhead (measured 0.41 -> 0.35 ms at the headline config).
 static int fwd5_plan(int M, int logd, int* rc_out, int* lpp_out = nullptr) {
-    static int l16 = -1;
-    if (l16 < 0) {
-        const char* e = getenv("SKB_LPP16");      // development switch: SKB_LPP16=0 disables the 16-lane variant
-        l16 = e ? atoi(e) : 1;
-    }
     if (lpp_out) *lpp_out = 32;
-    if (l16) {
+    {
         int rc = (M + 15) / 16, rcp = 1;
         while (rcp < rc) rcp <<= 1;
         if (fwd5_l16_shape_ok(rcp, logd)) {
@@ -246,8 +235,17 @@ static int fwd5_plan(int M, int logd, int* rc_out, int* lpp_out = nullptr) {
 
 int fwd5_warps_per_pair(int M, int logd, int* lpp) { return fwd5_plan(M, logd, nullptr, lpp); }
 
+// true if the fwd5 variant of this shape evaluates exp with the pre-scaled argument (SCALED in skb_fwd5.cuh)
+bool fwd5_scaled_exp(int M, int logd, int D) {
+    int rcp = 0, lpp = 32;
+    const int nw = fwd5_plan(M, logd, &rcp, &lpp);
+    if (nw != 1) return false;
+    const int dp2 = padded_dim(D) / 2, R = rcp << logd;
+    return rcp * dp2 <= ((lpp == 16 && R > 8) ? 12 : 8);
+}
+
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
-    if (!use_fwd5() || s1 || N < 4) return false;
+    if (s1 || N < 4) return false;
     if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
     const int Dp = padded_dim(D);
     if (Dp != 4 && Dp != 6 && Dp != 10) return false;
@@ -269,12 +267,7 @@ static void fill_v5_constants(KArgs& args, int logd) {
 static bool adjoint5_shape_ok(int rc, int logd) { return (rc == 1 && logd >= 1 && logd <= 3) || (rc == 2 && logd >= 1 && logd <= 2); }
 
 bool adjoint5_applies(int kind, int M, int N, int D, int logd, bool s1) {
-    static int on = -1;
-    if (on < 0) {
-        const char* e = getenv("SKB_ADJ5");       // development switch: SKB_ADJ5=0 forces the v4 adjoint kernels
-        on = e ? atoi(e) : 1;
-    }
-    if (!on || s1 || N < 4) return false;
+    if (s1 || N < 4) return false;
     if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
     const int Dp = padded_dim(D);
     if (Dp != 4 && Dp != 6 && Dp != 10) return false;
@@ -300,6 +293,11 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
     const int nw = fwd5_plan(args.M, logd, &rcp, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
     fill_v5_constants(args, logd);
+    if (fwd5_scaled_exp(args.M, logd, args.D)) {
+        // single-warp forward variants with the x rows in registers: exp argument in units of c = ln2 / 2048 (exp_scaled5): e^(r c) - 1 = r (c + r (c^2/2 + r c^3/6))
+        const double c = 0.693147180559945309417232121458 / 2048.0;
+        args.ek = c; args.e4 = c * c / 2.0; args.e3 = c * c * c / 6.0;
+    }
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int rc = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (rc) return rc;
@@ -315,6 +313,126 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
         rc = table[kind == KIND_RBF ? 1 : 0][nw == 1 ? 0 : (nw == 2 ? 1 : 2)](rcp, logd, args.Dp / 2, args, st);
     if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
     return rc;
+}
+
+// ---- tile forward kernel (skb_tile.cuh) --------------------------------------------------------------------
+static int g_tile_mode = -1;
+void set_tile_mode(int mode) { g_tile_mode = mode; }
+
+static const int kTileW = 8, kTileR = 16;     // warps per block (strips per band), fine rows per strip
+
+static bool tile_shape_ok(int logd) { return logd >= 1 && logd <= 3; }   // SKB_TILE_SHAPES: RC = 16 >> logd
+
+static long tile_count(int A, int B, int pairs) {
+    const long nta = (A + 31) / 32;
+    return pairs == PAIRS_BATCH ? nta : nta * (long)B;
+}
+
+bool tile_applies(int kind, int A, int B, int M, int N, int D, int logd, bool s1, int pairs) {
+    if (g_tile_mode == 0 || s1 || N < 16) return false;     // N - 1 >= TILE_RD_MAX + 1 (skb_tile.cuh)
+    if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
+    if (pairs != PAIRS_GRAM && pairs != PAIRS_BATCH) return false;
+    const int Dp = padded_dim(D);
+    if (Dp != 4 && Dp != 6 && Dp != 10) return false;
+    if (!tile_shape_ok(logd)) return false;
+    const long MMf = (long)(M - 1) << logd;
+    const long strips = (MMf + kTileR - 1) / kTileR;
+    const long ntiles = tile_count(A, B, pairs);
+    const long nbands = (strips + kTileW - 1) / kTileW;
+    if (ntiles * nbands > 0x3fffffffL) return false;
+    // opt-in only: at every BASELINE config the tile kernel is slower than fwd5_kernel so far
+    return g_tile_mode == 1;
+}
+
+double tile_arg_scale() { return 2048.0 / 0.693147180559945309417232121458; }
+
+static size_t tile_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t tile_workspace_bytes(int A, int B, int M, int N, int logd, int pairs) {
+    const long MMf = (long)(M - 1) << logd;
+    const long strips = (MMf + kTileR - 1) / kTileR;
+    const size_t ntiles = (size_t)tile_count(A, B, pairs), nbands = (size_t)((strips + kTileW - 1) / kTileW);
+    const size_t F = (size_t)1 << logd, NS = (size_t)(N - 1);
+    return tile_align(ntiles * NS * 32 * sizeof(double)) + tile_align(ntiles * (nbands - 1) * NS * (F / 2 + 1) * 32 * sizeof(double2)) +
+           tile_align(ntiles * (nbands - 1) * sizeof(unsigned int) + 4);
+}
+
+template <int KIND>
+__global__ void tile_d0_zero_kernel(const TArgs p, int Dp, double inv_s, long nready);
+
+int launch_tile_forward(int kind, int logd, const KArgs& a, void* tile_ws, cudaStream_t st) {
+    if (!tile_shape_ok(logd) || !tile_ws || !a.counter) return SKB_ERR_UNSUPPORTED;
+    TArgs t;
+    memset(&t, 0, sizeof(t));
+    const long MMf = (long)(a.M - 1) << logd;
+    const long strips = (MMf + kTileR - 1) / kTileR;
+    t.Xp = a.Xp; t.Yp = a.Yp; t.out = a.out; t.counter = a.counter;
+    t.A = a.A; t.B = a.B; t.M = a.M; t.N = a.N; t.pairs = a.pairs;
+    t.nta = (a.A + 31) / 32;
+    t.ntiles = (int)tile_count(a.A, a.B, a.pairs);
+    t.nbands = (int)((strips + kTileW - 1) / kTileW);
+    t.njobs = t.ntiles * t.nbands;
+    t.kscale = fwd5_kscale(logd);
+    t.sqrt3 = sqrt(3.0);
+    const double c = 0.693147180559945309417232121458 / 2048.0;
+    t.c1 = c; t.c2 = c * c / 2.0; t.c3 = c * c * c / 6.0;
+    const size_t F = (size_t)1 << logd, NS = (size_t)(a.N - 1);
+    char* w = (char*)tile_ws;
+    t.d0 = (const double*)w;
+    w += tile_align((size_t)t.ntiles * NS * 32 * sizeof(double));
+    t.bnd = (double2*)w;
+    w += tile_align((size_t)t.ntiles * (t.nbands - 1) * NS * (F / 2 + 1) * 32 * sizeof(double2));
+    t.ready = (unsigned int*)w;
+    int rc = a.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+    if (rc) return rc;
+    {
+        // top boundary of band 0 (+ zeroing of the band hand-off counters)
+        const long n = (long)t.ntiles * (long)NS * 32;
+        const long nready = (long)t.ntiles * (t.nbands - 1);
+        const unsigned grid = (unsigned)(((n > nready ? n : nready) + 255) / 256);
+        if (kind == KIND_RBF) tile_d0_zero_kernel<KIND_RBF><<<grid, 256, 0, st>>>(t, a.Dp, 1.0 / tile_arg_scale(), nready);
+        else tile_d0_zero_kernel<KIND_LINEAR><<<grid, 256, 0, st>>>(t, a.Dp, 1.0, nready);
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+    rc = kind == KIND_RBF ? launch_group_tile_rbf(kTileR >> logd, logd, a.Dp / 2, t, st)
+                          : launch_group_tile_lin(kTileR >> logd, logd, a.Dp / 2, t, st);
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+    return rc;
+}
+
+template <int KIND>
+__global__ void tile_d0_zero_kernel(const TArgs p, int Dp, double inv_s, long nready) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < nready) p.ready[idx] = 0u;
+    const int lane = (int)(idx & 31);
+    const long tc = idx >> 5;
+    const int NS = p.N - 1;
+    if (tc >= (long)p.ntiles * NS) return;
+    const int tile = (int)(tc / NS), c = (int)(tc - (long)tile * NS);
+    int a, b;
+    if (p.pairs == PAIRS_BATCH) {
+        a = b = tile * 32 + lane;
+    } else {
+        b = tile / p.nta;
+        a = (tile - b * p.nta) * 32 + lane;
+    }
+    a = a < p.A ? a : p.A - 1;
+    b = b < p.B ? b : p.B - 1;
+    const double* x = p.Xp + ((size_t)a * p.M) * Dp;
+    const double* y0 = p.Yp + ((size_t)b * p.N + c) * Dp;
+    const double* y1 = y0 + Dp;
+    double a0 = x[0] + y0[0], a1 = x[0] + y1[0];
+    for (int k = 1; k < Dp; ++k) {
+        a0 = fma(x[k], y0[k], a0);
+        a1 = fma(x[k], y1[k], a1);
+    }
+    if (KIND == KIND_RBF) {
+        a0 = p.kscale * exp(a0 * inv_s);
+        a1 = p.kscale * exp(a1 * inv_s);
+    }
+    const_cast<double*>(p.d0)[idx] = a1 - a0;
 }
 
 int launch_solver(int mode, int kind, int logd, bool exact, KArgs args, cudaStream_t st) {

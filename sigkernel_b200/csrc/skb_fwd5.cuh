@@ -69,6 +69,26 @@ __device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ 
     return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB - 1)) * 4096, __double2loint(v));
 }
 
+// Forward mode (MODE 0): the exp argument arrives pre-scaled by 2048 / ln 2 (folded into the prepared rows), so the
+// range reduction is three additions (no hi/lo split of ln 2) and a 2^11-entry table leaves a degree-3 polynomial:
+// 7 DP instructions instead of 9.  The guard clamps xs to >= -2031616 (x >= -687.6); NaN passes through.
+constexpr int EXP_TAB5 = 2048;
+__device__ __forceinline__ double exp_scaled5(double xs, const double* __restrict__ tab, const KArgs& p) {
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+    const unsigned hi = min((unsigned)__double2hiint(xs), 0xC13F0000u);
+    const double xc = __hiloint2double((int)hi, __double2loint(xs));
+    const double t = xc + MAGIC;
+    const double nf = t - MAGIC;                         // nearest integer = 2048 n + j
+    const double r = xc - nf;                            // exact, |r| <= 1/2
+    double q = fma(r, p.e3, p.e4);                       // e4 = c^2/2, e3 = c^3/6, ek = c = ln2 / 2048 (forward mode)
+    q = fma(q, r, p.ek);
+    q = q * r;                                           // e^(r c) - 1, truncation 3.4e-17
+    const int ti = __double2loint(t);
+    const double tj = tab[ti & (EXP_TAB5 - 1)];
+    const double v = fma(tj, q, tj);
+    return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB5 - 1)) * 512, __double2loint(v));
+}
+
 // shared-memory accesses of the neighbour exchange: 32-bit shared addresses with compile-time offsets, so that
 // the per-step address arithmetic disappears (the buffer index is the position in the 3x unrolled loop)
 template <int OFF>
@@ -153,7 +173,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     const int first_job = blockIdx.x * NSTR + sid;
     const bool has_job = first_job < p.njobs;
 
-    __shared__ double etab[EXP_TAB];             // RBF: kscale * 2^(j/256)
+    constexpr int Fq = 1 << LOGD, Rq = RC * Fq;
+    constexpr bool XREGq = (RC * DP2 <= ((LPP == 16 && Rq > 8) ? 12 : 8));
+    // pre-scaled exp argument + 2^11 table: single-warp forward variants whose x rows live in registers (with the x rows
+    // in shared memory the 16 KB table would cost a resident block per SM).  Keep in sync with fwd5_scaled_exp().
+    constexpr bool SCALED = MODE == 0 && NW == 1 && XREGq;
+    constexpr int ETAB = SCALED ? EXP_TAB5 : EXP_TAB;
+    __shared__ double etab[ETAB];                // RBF: kscale * 2^(j/ETAB)
     __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset, -) in bytes
     // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
     // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
@@ -168,7 +194,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     __shared__ double2 tx[3][H][NL + 1];
     __shared__ double dx[3][NL + 1];
     if (KIND == KIND_RBF) {
-        for (int j = glane; j < EXP_TAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / EXP_TAB));
+        for (int j = glane; j < ETAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / ETAB));
     }
 
     // ---- job stream -------------------------------------------------------------------------------
@@ -533,7 +559,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 xv = XREG ? xr[XREG ? rc : 0][i] : (XSM ? xs_s[XSM ? rc * DP2 + i : 0][XSM ? glane : 0] : ldg2(xrow[(XREG || XSM) ? 0 : rc] + 2 * i));
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
-            if (KIND == KIND_RBF) acc = exp_neg5(acc, etab, p);
+            if (KIND == KIND_RBF) acc = SCALED ? exp_scaled5(acc, etab, p) : exp_neg5(acc, etab, p);
             dnew[rc] = REVG ? klast[rc] : acc - klast[rc];      // REV_GRAD: the history rotates k itself
             klast[rc] = acc;
         }

@@ -92,6 +92,7 @@ int launch_group_fwd5_lin_l16(int rc, int logd, int dp2, const KArgs&, cudaStrea
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1);
 // warps per pair fwd5 would use (0: not covered); *lpp (if given) receives the lanes per pair (32 or 16)
 int fwd5_warps_per_pair(int M, int logd, int* lpp = nullptr);
+bool fwd5_scaled_exp(int M, int logd, int D);
 // scale the static kernel is produced with on the fwd5 path (Linear: folded into the prepared X rows)
 double fwd5_kscale(int logd);
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st);
@@ -102,5 +103,21 @@ int launch_group_adj5_rbf_store(int rc, int logd, int dp2, const KArgs&, cudaStr
 int launch_group_adj5_rbf_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_adj5_lin_store(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_adj5_lin_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+
+// ---- tile forward kernel (skb_tile.cuh): one pair per lane, one strip per warp, W-warp pipelines ---------------
+struct TArgs;
+// true if skb_sigkernel_fwd should take the tile path: fused kind, scheme S2, GRAM / BATCH pairs, N >= 4, strip shape
+// instantiated, and enough (tile, strip) units to fill the GPU
+bool tile_applies(int kind, int A, int B, int M, int N, int D, int logd, bool s1, int pairs);
+// bytes of the tile path's part of the forward workspace (top-boundary differences, band boundaries, ready counters)
+size_t tile_workspace_bytes(int A, int B, int M, int N, int logd, int pairs);
+// scale of the prepared rows on the tile path: the exp argument arrives multiplied by 2048 / ln 2 (RBF)
+double tile_arg_scale();
+// args: Xp, Yp, out, counter (zeroed), A, B, M, N, D, Dp, pairs filled; tile_ws = tile_workspace_bytes() bytes
+int launch_tile_forward(int kind, int logd, const KArgs& args, void* tile_ws, cudaStream_t st);
+int launch_group_tile_rbf(int rc, int logd, int dp2, const TArgs&, cudaStream_t);
+int launch_group_tile_lin(int rc, int logd, int dp2, const TArgs&, cudaStream_t);
+// development / tuning knob (process-wide): 0 = never, 1 = whenever the shape is instantiated, -1 = default heuristic
+void set_tile_mode(int mode);
 
 }  // namespace skb

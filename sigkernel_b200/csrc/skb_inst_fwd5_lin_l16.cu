@@ -7,7 +7,7 @@ template <int KIND, int RC, int LOGD, int DP2>
 static int launch_l16(const KArgs& a, cudaStream_t st) {
     constexpr int MINB = (RC << LOGD) <= 8 ? 16 : 8, UNR = 3;     // 16-row strips need ~180 registers
     int wpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() : MINB;
-    if (wpsm > MINB) wpsm = MINB;
+    if (wpsm > 16) wpsm = 16;        // an explicit skb_set_warps_per_sm() may exceed the default residency (tuning)
     long nb = (long)sm_count() * wpsm;
     const long need = ((long)a.njobs + 1) / 2;                   // two pair streams per warp
     if (nb > need) nb = need;

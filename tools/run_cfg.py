@@ -12,6 +12,8 @@ CFG = {"cfg2": (64, 64, 32, 3, 1), "cfg3": (128, 128, 64, 5, 2), "cfg4f": (128, 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mode = sys.argv[3] if len(sys.argv) > 3 else "fwd"
+if os.environ.get('SKB_TILE_MODE'):
+    skb._lib.lib.skb_set_tile_mode(int(os.environ['SKB_TILE_MODE']))
 A, B, L, D, d = CFG[name]
 g = torch.Generator().manual_seed(0)
 X = torch.rand((A, L, D), dtype=torch.float64, generator=g).cuda()
