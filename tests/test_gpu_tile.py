@@ -61,30 +61,26 @@ def test_tile_batch_vs_oracle(skb, O, tile_on):
     assert fwd_err(got.cpu().numpy(), ref) <= FWD_TOL
 
 
-def test_tile_is_the_default_at_the_headline_config_and_agrees_with_fwd5(skb):
-    """BASELINE configs[2] (128 x 128, len 64, dim 5, dyadic 2): the default plan is the tile kernel; it agrees with
-    fwd5_kernel to 1e-12 and with the reference fixture (leading 8 x 8 block) to the north_star tolerance."""
+def test_tile_agrees_with_fwd5_at_the_headline_config(skb):
+    """BASELINE configs[2] (128 x 128, len 64, dim 5, dyadic 2): the tile kernel agrees with fwd5_kernel (the default
+    plan) to 1e-12 and with the reference fixture (leading 8 x 8 block) to the north_star tolerance."""
     g = torch.Generator().manual_seed(0)
     X = torch.rand((128, 64, 5), dtype=torch.float64, generator=g)
     Y = torch.rand((128, 64, 5), dtype=torch.float64, generator=g)
     lib = skb._lib.lib
-    lib.skb_set_tile_mode(0)
     G5 = skb.ops.sigkernel_forward(X.cuda(), Y.cuda(), "rbf", 0.5, 2, "gram")
-    lib.skb_set_tile_mode(-1)
-    Gt = skb.ops.sigkernel_forward(X.cuda(), Y.cuda(), "rbf", 0.5, 2, "gram")
+    lib.skb_set_tile_mode(1)
+    try:
+        Gt = skb.ops.sigkernel_forward(X.cuda(), Y.cuda(), "rbf", 0.5, 2, "gram")
+        Gs = skb.ops.sigkernel_forward(X[32:64].cuda(), Y[5:7].cuda(), "rbf", 0.5, 2, "gram")
+    finally:
+        lib.skb_set_tile_mode(-1)
     assert fwd_err(Gt.cpu().numpy(), G5.cpu().numpy()) <= 1e-12
     meta, z = load_golden("cfg3_gram_rbf")
-    g2 = torch.Generator().manual_seed(0)
-    X2 = torch.rand((128, 64, 5), dtype=torch.float64, generator=g2)
-    Y2 = torch.rand((128, 64, 5), dtype=torch.float64, generator=g2)
-    assert np.array_equal(X2[:8].numpy(), z["X"])
-    Gd = skb.SigKernel(skb.RBFKernel(0.5), 2).compute_Gram(X2.cuda(), Y2.cuda())
-    assert fwd_err(Gd[:8, :8].cpu().numpy(), z["G"]) <= FWD_TOL
+    assert np.array_equal(X[:8].numpy(), z["X"])
+    assert fwd_err(Gt[:8, :8].cpu().numpy(), z["G"]) <= FWD_TOL
     # row-block invariance: a tile computed inside a bigger batch equals the same pairs alone
-    lib.skb_set_tile_mode(1)
-    Gs = skb.ops.sigkernel_forward(X2[32:64].cuda(), Y2[5:7].cuda(), "rbf", 0.5, 2, "gram")
-    lib.skb_set_tile_mode(-1)
-    assert torch.equal(Gs, Gd[32:64, 5:7])
+    assert torch.equal(Gs, Gt[32:64, 5:7])
 
 
 def test_tile_overflow_stays_in_its_pair(skb, tile_on):
