@@ -74,6 +74,11 @@ void skb_set_warps_per_sm(int warps);
  * (the tile kernel is slower than fwd5_kernel at every BASELINE config so far). */
 void skb_set_tile_mode(int mode);
 
+/* Tuning / test knob (process-wide, default -1): which kernels serve the backward entry points.  -1 = adjoint by
+ * reconstruction (16 lanes per pair where instantiated) with the stored-grid kernels queued as a device-side fallback,
+ * 0 = stored-grid kernels only (round-1 behaviour), 1 = reconstruction with 32 lanes per pair only. */
+void skb_set_adjoint_mode(int mode);
+
 /* Measurement hook (per calling thread): when both are non-NULL, every solver launch made by this thread records
  * `start` immediately before and `stop` immediately after the solver kernel on the launch stream
  * (cudaEvent_t passed as void*), so a caller can time the dominant kernel alone, without the
@@ -92,7 +97,9 @@ int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, voi
  *                                               5 / 6 / 7 = fwd5_kernel with 1 / 2 / 4 warps per pair;
  *   skb_adjoint_plan  (skb_sigkernel_fwd_bwd): -4 (SKB_ERR_UNSUPPORTED) = shape not covered by the backward,
  *                                               1 = solver_kernel store / reversed modes (v4),
- *                                               5 = fwd5_kernel store / reversed modes.
+ *                                               5 = fwd5_kernel store / reversed modes,
+ *                                               6 = adjoint by reconstruction (fwd5_kernel MODE_FWD_EMIT + MODE_REV_RECON;
+ *                                                   no stored grid, (len_x - 1) 2^d <= 1024 at dyadic order <= 2).
  * Negative values are SKB_ERR_* codes for bad arguments. */
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
 int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
@@ -108,10 +115,15 @@ size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_ord
 /* from_static (A,B,M,N as passed there) / solve_increments (A = B = P, M = MM+1, N = NN+1, dyadic_order 0,
  * pairs = SKB_PAIRS_BATCH) */
 size_t skb_aux_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs);
-/* Recommended size for the backward entry points: room for the forward grids of all pairs,
- * capped at 8 GiB.  Any size >= the room for ONE pair's grid is accepted: the pairs are then
- * processed in chunks that fit. */
+/* Recommended size for skb_sigkernel_fwd_bwd / skb_sigkernel_sensitivity_from_static: prepared paths, the boundary
+ * context of the adjoint by reconstruction, and room for the forward grids of the stored-grid kernels (all pairs, capped
+ * at 8 GiB; 1 GiB when they are only the fallback of the reconstruction).  Any size >= the fixed part + ONE pair's grid
+ * is accepted: the pairs are then processed in chunks that fit. */
 size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
+/* Boundary context written by skb_sigkernel_fwd_ctx and read by skb_sigkernel_bwd_vjp: the last row and the last column of
+ * every pair's solution grid ((NN + 1) + (MM + 1) doubles per pair, rounded up to multiples of 4). */
+size_t skb_ctx_bytes(int A, int B, int M, int N, int dyadic_order, int pairs);
+size_t skb_bwd_vjp_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs);
 
 /* ---- forward: fused static kernel + increments + dyadic refinement + PDE solve ----- */
 
@@ -171,6 +183,48 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
                           int static_kind, double static_param, int scheme, int pairs,
                           double* out, double* grad_points,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same backward split in two, for callers that learn d loss / d K only later (torch.autograd's backward) and
+ * never want the (pairs, M, D) tensor:
+ *
+ * skb_sigkernel_fwd_ctx   out[pairs] as skb_sigkernel_fwd (GRAM, BATCH or SYM) plus the boundary context `ctx`
+ *                         (skb_ctx_bytes): all the reversed sweep needs from the forward solve.  Workspace:
+ *                         skb_fwd_workspace_bytes.  SKB_ERR_UNSUPPORTED if the shape is outside the reconstruction
+ *                         kernels (see skb_adjoint_plan == 6): use skb_sigkernel_fwd_bwd then.
+ * skb_sigkernel_bwd_vjp   reversed sweep over every ordered pair of `pairs` (GRAM or BATCH; `ctx_pairs` names the pair
+ *                         set of the forward call: SYM is allowed with GRAM here -- the pair (a, b), a > b, reads the
+ *                         transposed grid of (b, a)), contracted on the fly with d loss / d K:
+ *                             g[a, m, :] = sum_b coef(a, b) * d k(X_a, Y_b) / d X_a[m, :]
+ *                             gradX = (accumulate ? gradX : 0) + out_scale * (out_scale_dev ? *out_scale_dev : 1) * g
+ *                         coef = grad_out[pair] if grad_out != NULL, else (a == b ? w_diag : w_off) -- the closed forms of
+ *                         the MMD and the scoring rules (sigkernel.py:146-197), replacing sigkernel.py:405-416; out_scale
+ *                         carries the reference's factor 2 for Gram(X, X) (sigkernel.py:410-412), out_scale_dev (device,
+ *                         may be NULL) the upstream gradient of a scalar loss.  g is summed with fp64 atomics (the order
+ *                         over b varies from run to run).  grad_points (pairs, M, D) is also written if not NULL; one of
+ *                         gradX (A, M, D) and grad_points must be given.  Workspace: skb_bwd_vjp_workspace_bytes (smaller is accepted: without room for
+ *                         one pair's grid + gradients the stored-grid fallback is not queued; the flag word at byte 64 of
+ *                         the workspace is then the caller's to check -- non-zero = a rebuilt grid missed its boundary
+ *                         by more than 1e-10 and the result should be recomputed with skb_sigkernel_fwd_bwd).
+ */
+int skb_sigkernel_fwd_ctx(const void* X, const void* Y, int io_dtype,
+                          int A, int B, int M, int N, int D, int dyadic_order,
+                          int static_kind, double static_param, int scheme, int pairs,
+                          double* out, void* ctx, size_t ctx_bytes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype,
+                          int A, int B, int M, int N, int D, int dyadic_order,
+                          int static_kind, double static_param, int scheme, int pairs,
+                          const void* ctx, int ctx_pairs, const double* grad_out, double w_diag, double w_off,
+                          double out_scale, const double* out_scale_dev, int accumulate,
+                          double* gradX, double* grad_points,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* acc[0] = (accumulate ? acc[0] : 0) + sum_{a,b} w(a,b) G[a,b], w = w_diag on the diagonal and w_off elsewhere; G is the
+ * row-major (A, B) output of a GRAM / SYM call, or the A-vector of a BATCH call (every entry weighted w_diag): the
+ * reductions of compute_mmd / compute_distance / compute_scoring_rule (sigkernel.py:130-197), one launch per Gram. */
+int skb_gram_weighted_sum(const double* G, int A, int B, int pairs, double w_diag, double w_off, double* acc, int accumulate,
+                          void* stream);
 
 /*
  * Plugin path of the backward: coarse sensitivities

@@ -25,6 +25,12 @@ SYMBOLS = {
     "skb_version": (_i, []),
     "skb_set_warps_per_sm": (None, [_i]),
     "skb_set_tile_mode": (None, [_i]),
+    "skb_set_adjoint_mode": (None, [_i]),
+    "skb_ctx_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "skb_bwd_vjp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "skb_sigkernel_fwd_ctx": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "skb_sigkernel_bwd_vjp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "skb_gram_weighted_sum": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _i, _vp]),
     "skb_set_profile_events": (None, [_vp, _vp]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "skb_forward_plan": (_i, [_i, _i, _i, _i, _i, _i]),

@@ -6,7 +6,7 @@
 
 namespace skb {
 
-constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3;
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5;
 
 static thread_local int g_last_cuda = 0;
 
@@ -152,6 +152,49 @@ static int run_generic_forward(int src_kind, KArgs a, int d, bool exact, long nj
     return SKB_OK;
 }
 
+// ---- adjoint by reconstruction: layout of the boundary context (last row / last column of every pair's grid) ----
+static size_t ctx_row_doubles(int N, int d) { return ((((size_t)(N - 1)) << d) + 1 + 3) & ~(size_t)3; }
+static size_t ctx_col_doubles(int M, int d) { return ((((size_t)(M - 1)) << d) + 1 + 3) & ~(size_t)3; }
+static const size_t kFlagOffset = 64;            // the reconstruction flag lives in the counter block of the workspace
+static const double kReconTol = 1e-10;           // |rebuilt u[., 0] - 1| beyond this sends the call to the stored-grid kernels
+static const size_t kFallbackBudget = (size_t)1 << 30;
+
+static void set_ctx(KArgs& a, void* ctx, long njobs, int M, int N, int d) {
+    a.brow = (double*)ctx;
+    a.brow_stride = (long)ctx_row_doubles(N, d);
+    a.bcol = a.brow + (size_t)njobs * a.brow_stride;
+    a.bcol_stride = (long)ctx_col_doubles(M, d);
+}
+
+// acc += sum_{a,b} w(a,b) G[a,b] with w = w_diag on the diagonal, w_off elsewhere (row-major (A, B)): the reductions behind
+// the MMD, the distance and the scoring rules (sigkernel.py:130-197)
+__global__ void gram_reduce_kernel(const double* __restrict__ G, long n, int B, double w_diag, double w_off, double* __restrict__ acc) {
+    // B == 0: a vector of n batch entries, every one weighted w_diag
+    double s = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const bool dg = B == 0 || (i / B == i % B);
+        s = fma(dg ? w_diag : w_off, G[i], s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+
+// gradX = (accumulate ? gradX : 0) + scale * gtmp, scale = out_scale * (out_scale_dev ? *out_scale_dev : 1)
+__global__ void combine_kernel(double* __restrict__ gradX, const double* __restrict__ gtmp, size_t n, double out_scale,
+                               const double* __restrict__ out_scale_dev, int accumulate) {
+    const double sc = out_scale * (out_scale_dev ? *out_scale_dev : 1.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        gradX[i] = accumulate ? fma(sc, gtmp[i], gradX[i]) : sc * gtmp[i];
+}
+
+static int launch_combine(double* gradX, const double* gtmp, size_t n, double out_scale, const double* out_scale_dev, int accumulate,
+                          cudaStream_t st) {
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    combine_kernel<<<(unsigned)blocks, 256, 0, st>>>(gradX, gtmp, n, out_scale, out_scale_dev, accumulate);
+    return check_launch();
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -175,6 +218,7 @@ int skb_last_cuda_error(void) { return g_last_cuda; }
 int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
 void skb_set_tile_mode(int mode) { set_tile_mode(mode); }
+void skb_set_adjoint_mode(int mode) { set_adjoint_mode(mode); }
 void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme) {
@@ -195,6 +239,7 @@ int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
     if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (recon5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1)) return 6;
     if (solver_rows_per_lane(M, dyadic_order) < 0) return SKB_ERR_UNSUPPORTED;
     return adjoint5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) ? 5 : 1;
 }
@@ -219,19 +264,46 @@ size_t skb_aux_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int
     return w;
 }
 
-size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
-    if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || dyadic_order < 0) return 0;
-    const size_t per = grid_doubles_per_pair(M, N, dyadic_order) * sizeof(double);
-    if (per == 0) return 0;
+static bool recon_ok(int static_kind, int A, int B, int M, int N, int D, int d, int scheme) {
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
     const size_t Dp = (size_t)padded_dim(D);
-    const size_t fixed = kCounterBytes + 2 * align256((size_t)A * M * Dp * sizeof(double)) +
-                         2 * align256((size_t)B * N * Dp * sizeof(double)) +
-                         align256(front_pad_doubles(M, dyadic_order) * sizeof(double));
-    size_t jobs = (size_t)njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
-    size_t cap = kScratchBudget / per;
-    if (cap < 1) cap = 1;
-    if (jobs > cap) jobs = cap;
-    return fixed + align256(jobs * per);
+    return recon5_applies(kind, M, N, D, d, scheme == SKB_SCHEME_S1) && (size_t)A * M * Dp * sizeof(double) < ((size_t)1 << 32) &&
+           (size_t)B * N * Dp * sizeof(double) < ((size_t)1 << 32);
+}
+
+size_t skb_ctx_bytes(int A, int B, int M, int N, int dyadic_order, int pairs) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || dyadic_order < 0 || dyadic_order > 20) return 0;
+    return align256((size_t)njobs_of(A, B, pairs) * (ctx_row_doubles(N, dyadic_order) + ctx_col_doubles(M, dyadic_order)) * sizeof(double));
+}
+
+// fixed part: counter block, prepared paths in both orientations, [boundary context]; then the stored-grid scratch
+static size_t bwd_workspace_bytes(int A, int B, int M, int N, int D, int d, int pairs, bool with_ctx, bool with_vjp) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || d < 0) return 0;
+    const long nj = njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
+    const bool recon = recon_ok(SKB_STATIC_RBF, A, B, M, N, D, d, SKB_SCHEME_S2);
+    const size_t grid_b = grid_doubles_per_pair(M, N, d) * sizeof(double);
+    if (!recon && grid_b == 0) return 0;
+    const size_t Dp = (size_t)padded_dim(D);
+    size_t w = kCounterBytes + 2 * align256((size_t)A * M * Dp * sizeof(double)) + 2 * align256((size_t)B * N * Dp * sizeof(double));
+    if (recon && with_ctx) w += skb_ctx_bytes(A, B, M, N, d, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
+    if (with_vjp) w += align256((size_t)nj * sizeof(double)) + align256((size_t)A * M * D * sizeof(double));   // k of the fallback's forward pass; this call's gradient
+    if (grid_b != 0) {
+        const size_t per = grid_b + (with_vjp ? (size_t)M * D * sizeof(double) : 0);
+        size_t jobs = (size_t)nj;
+        size_t cap = (recon ? kFallbackBudget : kScratchBudget) / per;
+        if (cap < 1) cap = 1;
+        if (jobs > cap) jobs = cap;
+        w += align256(front_pad_doubles(M, d) * sizeof(double)) + align256(jobs * per) + 512;
+    }
+    return w;
+}
+
+size_t skb_bwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
+    return bwd_workspace_bytes(A, B, M, N, D, dyadic_order, pairs, true, false);
+}
+
+size_t skb_bwd_vjp_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
+    return bwd_workspace_bytes(A, B, M, N, D, dyadic_order, pairs, false, true);
 }
 
 int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
@@ -319,26 +391,47 @@ int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, in
                                workspace_bytes - kCounterBytes, (cudaStream_t)stream);
 }
 
-// shared driver of the two backward entry points: forward-with-store then reversed sweep, in chunks
-// of pairs whose forward grids fit the scratch part of the workspace
+// fused loss head on the stored-grid path: per-point gradients of a chunk go to a chunk-sized buffer and are contracted
+// with d loss / d K right after the chunk's reversed sweep
+struct VjpOpts {
+    const double* gout;
+    double w_diag, w_off;
+    double* gradX;
+};
+
+// shared driver of the backward entry points: forward-with-store then reversed sweep, in chunks of pairs whose forward
+// grids (and, with a loss head, per-point gradients) fit the scratch part of the workspace.  fa.cond / ra.cond (if set)
+// make every launch a no-op unless the flag they point to is raised.
 static int run_adjoint(int kind, int rev_mode, KArgs fa, KArgs ra, int d, long njobs, double* scratch_base,
-                       size_t scratch_bytes, cudaStream_t st, bool v5 = false) {
-    const size_t per = grid_doubles_per_pair(fa.M, fa.N, d) * sizeof(double);
+                       size_t scratch_bytes, cudaStream_t st, bool v5 = false, const VjpOpts* vjp = nullptr) {
+    const size_t grid_b = grid_doubles_per_pair(fa.M, fa.N, d) * sizeof(double);
+    const size_t gp_b = vjp ? (size_t)fa.M * fa.D * sizeof(double) : 0;
+    const size_t per = grid_b + gp_b;
     const size_t pad = front_pad_doubles(fa.M, d) * sizeof(double);
-    if (per == 0) return SKB_ERR_UNSUPPORTED;
-    if (scratch_bytes < align256(pad) + per) return SKB_ERR_WORKSPACE;
-    long chunk = (long)((scratch_bytes - align256(pad)) / per);
+    if (grid_b == 0) return SKB_ERR_UNSUPPORTED;
+    if (scratch_bytes < align256(pad) + per + 256) return SKB_ERR_WORKSPACE;
+    long chunk = (long)((scratch_bytes - align256(pad) - 256) / per);
     if (chunk > njobs) chunk = njobs;
     double* grid = (double*)((char*)scratch_base + align256(pad));
+    double* gpbuf = vjp ? (double*)((char*)grid + align256((size_t)chunk * grid_b)) : nullptr;
+    if (vjp && (char*)gpbuf + (size_t)chunk * gp_b > (char*)scratch_base + scratch_bytes) --chunk;
+    if (chunk < 1) return SKB_ERR_WORKSPACE;
     for (long j0 = 0; j0 < njobs; j0 += chunk) {
         const int nj = (int)(njobs - j0 < chunk ? njobs - j0 : chunk);
         fa.job0 = ra.job0 = j0;
         fa.njobs = ra.njobs = nj;
         fa.scratch = ra.scratch = grid;
+        fa.counter_clean = ra.counter_clean = 0;
+        if (vjp) ra.grad = gpbuf - (size_t)j0 * fa.M * fa.D;      // the kernels index per-point gradients by the global pair index
         int rc = v5 ? launch_adjoint5(MODE_FWD_STORE, kind, d, fa, st) : launch_solver(MODE_FWD_STORE, kind, d, false, fa, st);
         if (rc) return rc;
         rc = v5 ? launch_adjoint5(rev_mode, kind, d, ra, st) : launch_solver(rev_mode, kind, d, false, ra, st);
         if (rc) return rc;
+        if (vjp) {
+            rc = launch_vjp_accumulate(gpbuf, j0, nj, fa.A, fa.B, fa.M, fa.D, fa.pairs, vjp->gout, vjp->w_diag, vjp->w_off,
+                                       vjp->gradX, ra.cond, st);
+            if (rc) return rc;
+        }
     }
     return SKB_OK;
 }
@@ -358,10 +451,119 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     cudaStream_t st = (cudaStream_t)stream;
     const int Dp = padded_dim(D);
     const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
-    const size_t fixed = kCounterBytes + 2 * xb + 2 * yb;
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    const bool recon = recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme);
+    const bool stored = solver_rows_per_lane(M, dyadic_order) >= 0;
+    if (!recon && !stored) return SKB_ERR_UNSUPPORTED;
+    const size_t ctxb = recon ? skb_ctx_bytes(A, B, M, N, dyadic_order, pairs) : 0;
+    const size_t fixed = kCounterBytes + 2 * xb + 2 * yb + ctxb;
     if (workspace_bytes < fixed) return SKB_ERR_WORKSPACE;
     char* w = (char*)workspace;
     unsigned int* counter = (unsigned int*)w;
+    unsigned int* flag = (unsigned int*)(w + kFlagOffset);
+    double* Xp = (double*)(w + kCounterBytes);
+    double* Yp = (double*)(w + kCounterBytes + xb);
+    double* Xr = (double*)(w + kCounterBytes + xb + yb);
+    double* Yr = (double*)(w + kCounterBytes + 2 * xb + yb);
+    void* ctx = w + kCounterBytes + 2 * xb + 2 * yb;
+    double cx, nsc;
+    prep_factors(static_kind, static_param, cx, nsc);
+    const int kind5 = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    const bool v5 = adjoint5_applies(kind5, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
+                    (size_t)A * M * Dp * sizeof(double) < ((size_t)1 << 32) && (size_t)B * N * Dp * sizeof(double) < ((size_t)1 << 32);
+    // (the stored-grid fallback of a reconstruction call must read the same prepared rows: it then needs the v5 kernels)
+    const bool fallback = recon && stored && (kind5 != KIND_LINEAR || v5) &&
+                          workspace_bytes >= fixed + align256(front_pad_doubles(M, dyadic_order) * sizeof(double)) +
+                                                 grid_doubles_per_pair(M, N, dyadic_order) * sizeof(double) + 512;
+    if ((recon || v5) && kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on the v5 paths
+    rc = check_cuda(cudaMemsetAsync(w, 0, kCounterBytes, st));
+    if (rc) return rc;
+    rc = launch_prep2(X, Y, io_dtype, Xp, Xr, Yp, Yr, A, M, B, N, D, Dp, cx, nsc, nullptr, st);
+    if (rc) return rc;
+
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    fa.Xp = Xp; fa.Yp = Yp; fa.out = out; fa.counter = counter; fa.Dp = Dp; fa.D = D;
+    fa.njobs = (int)nj;
+    KArgs ra = fa;
+    ra.Xp = Xr; ra.Yp = Yr; ra.out = nullptr; ra.grad = grad_points;
+    ra.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
+    if (recon) {
+        set_ctx(fa, ctx, nj, M, N, dyadic_order);
+        set_ctx(ra, ctx, nj, M, N, dyadic_order);
+        fa.counter_clean = 1;
+        rc = launch_recon5(MODE_FWD_EMIT, kind5, dyadic_order, fa, st);
+        if (rc) return rc;
+        ra.flag = flag; ra.recon_tol = kReconTol;
+        rc = launch_recon5(MODE_REV_RECON, kind5, dyadic_order, ra, st);
+        if (rc) return rc;
+        if (!fallback) return SKB_OK;
+        fa.cond = ra.cond = flag;            // queued behind a device-side test of the flag
+    }
+    return run_adjoint(kind5, MODE_REV_GRAD, fa, ra, dyadic_order, nj, (double*)(w + fixed), workspace_bytes - fixed, st, v5);
+}
+
+int skb_sigkernel_fwd_ctx(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D, int dyadic_order,
+                          int static_kind, double static_param, int scheme, int pairs, double* out, void* ctx,
+                          size_t ctx_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
+    if (rc) return rc;
+    if (D <= 0) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
+    if (!X || !Y || !out || !ctx) return SKB_ERR_NULL;
+    if (!recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme)) return SKB_ERR_UNSUPPORTED;
+    if (ctx_bytes < skb_ctx_bytes(A, B, M, N, dyadic_order, pairs)) return SKB_ERR_WORKSPACE;
+    const int Dp = padded_dim(D);
+    const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
+    if (!workspace || workspace_bytes < kCounterBytes + xb + yb) return SKB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    unsigned int* counter = (unsigned int*)w;
+    double* Xp = (double*)(w + kCounterBytes);
+    double* Yp = (double*)(w + kCounterBytes + xb);
+    double cx, nsc;
+    prep_factors(static_kind, static_param, cx, nsc);
+    const int kind5 = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    if (kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);
+    rc = launch_prep2(X, Y, io_dtype, Xp, nullptr, Yp, nullptr, A, M, B, N, D, Dp, cx, nsc, counter, st);
+    if (rc) return rc;
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    fa.Xp = Xp; fa.Yp = Yp; fa.out = out; fa.counter = counter; fa.Dp = Dp; fa.D = D;
+    fa.njobs = (int)nj;
+    fa.counter_clean = 1;
+    set_ctx(fa, ctx, nj, M, N, dyadic_order);
+    return launch_recon5(MODE_FWD_EMIT, kind5, dyadic_order, fa, st);
+}
+
+int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D, int dyadic_order,
+                          int static_kind, double static_param, int scheme, int pairs, const void* ctx, int ctx_pairs,
+                          const double* grad_out, double w_diag, double w_off, double out_scale, const double* out_scale_dev,
+                          int accumulate, double* gradX, double* grad_points,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
+    if (rc) return rc;
+    if (pairs == SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;          // the reversed sweep runs over every ordered pair
+    if (ctx_pairs != pairs && !(ctx_pairs == SKB_PAIRS_SYM && pairs == SKB_PAIRS_GRAM && A == B && M == N)) return SKB_ERR_BAD_ENUM;
+    if (D <= 0) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
+    if (!X || !Y || !ctx || (!gradX && !grad_points)) return SKB_ERR_NULL;
+    if (!recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme)) return SKB_ERR_UNSUPPORTED;
+    const int Dp = padded_dim(D);
+    const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
+    const long nj = njobs_of(A, B, pairs);
+    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    const size_t kb = align256((size_t)nj * sizeof(double));
+    const size_t gb = align256((size_t)A * M * D * sizeof(double));       // gradient of this call before scaling / accumulation
+    const size_t fixed = kCounterBytes + 2 * xb + 2 * yb + gb;
+    if (!workspace || workspace_bytes < fixed) return SKB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    unsigned int* counter = (unsigned int*)w;
+    unsigned int* flag = (unsigned int*)(w + kFlagOffset);
     double* Xp = (double*)(w + kCounterBytes);
     double* Yp = (double*)(w + kCounterBytes + xb);
     double* Xr = (double*)(w + kCounterBytes + xb + yb);
@@ -369,20 +571,67 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
     const int kind5 = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
-    const bool v5 = adjoint5_applies(kind5, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
-                    (size_t)A * M * Dp * sizeof(double) < ((size_t)1 << 32) && (size_t)B * N * Dp * sizeof(double) < ((size_t)1 << 32);
-    if (v5 && kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);   // k is produced pre-scaled on the v5 path
+    if (kind5 == KIND_LINEAR) cx *= fwd5_kscale(dyadic_order);
+    const bool v5 = adjoint5_applies(kind5, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1);
+    const bool stored = solver_rows_per_lane(M, dyadic_order) >= 0 && (kind5 != KIND_LINEAR || v5);
+    const size_t per = grid_doubles_per_pair(M, N, dyadic_order) * sizeof(double) + (size_t)M * D * sizeof(double);
+    const bool fallback = stored && workspace_bytes >= fixed + kb + align256(front_pad_doubles(M, dyadic_order) * sizeof(double)) + per + 768;
+    rc = check_cuda(cudaMemsetAsync(w, 0, kCounterBytes, st));
+    if (rc) return rc;
+    double* gtmp = (double*)(w + kCounterBytes + 2 * xb + 2 * yb);
+    if (gradX) {
+        rc = check_cuda(cudaMemsetAsync(gtmp, 0, (size_t)A * M * D * sizeof(double), st));
+        if (rc) return rc;
+    }
     rc = launch_prep2(X, Y, io_dtype, Xp, Xr, Yp, Yr, A, M, B, N, D, Dp, cx, nsc, nullptr, st);
     if (rc) return rc;
-
-    const long nj = njobs_of(A, B, pairs);
-    if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
-    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
-    fa.Xp = Xp; fa.Yp = Yp; fa.out = out; fa.counter = counter; fa.Dp = Dp; fa.D = D;
-    KArgs ra = fa;
-    ra.Xp = Xr; ra.Yp = Yr; ra.out = nullptr; ra.grad = grad_points;
+    KArgs ra = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    ra.Xp = Xr; ra.Yp = Yr; ra.counter = counter; ra.Dp = Dp; ra.D = D;
+    ra.njobs = (int)nj;
+    ra.counter_clean = 1;
+    ra.grad = grad_points;
     ra.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
-    return run_adjoint(kind5, MODE_REV_GRAD, fa, ra, dyadic_order, nj, (double*)(w + fixed), workspace_bytes - fixed, st, v5);
+    set_ctx(ra, const_cast<void*>(ctx), njobs_of(A, B, ctx_pairs), M, N, dyadic_order);
+    ra.bsym = ctx_pairs == SKB_PAIRS_SYM && pairs != SKB_PAIRS_SYM;
+    ra.flag = flag; ra.recon_tol = kReconTol;
+    ra.gout = grad_out; ra.gradX = gradX ? gtmp : nullptr; ra.w_diag = w_diag; ra.w_off = w_off;
+    rc = launch_recon5(MODE_REV_RECON, kind5, dyadic_order, ra, st);
+    if (rc) return rc;
+    if (!fallback) return gradX ? launch_combine(gradX, gtmp, (size_t)A * M * D, out_scale, out_scale_dev, accumulate, st) : SKB_OK;
+    // stored-grid fallback behind a device-side test of the flag: forward with store, reversed sweep, loss head
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    fa.Xp = Xp; fa.Yp = Yp; fa.out = (double*)(w + fixed); fa.counter = counter; fa.Dp = Dp; fa.D = D;
+    KArgs rb = fa;
+    rb.Xp = Xr; rb.Yp = Yr; rb.out = nullptr; rb.grad = grad_points;
+    rb.gscale = ra.gscale;
+    fa.cond = rb.cond = flag;
+    VjpOpts vo = {grad_out, w_diag, w_off, gtmp};
+    if (gradX) {
+        rc = launch_cond_zero(gtmp, (size_t)A * M * D, flag, st);
+        if (rc) return rc;
+    }
+    // (with grad_points requested the fallback writes them in place and the loss head reads them back chunk by chunk)
+    rc = run_adjoint(kind5, MODE_REV_GRAD, fa, rb, dyadic_order, nj, (double*)(w + fixed + kb), workspace_bytes - fixed - kb, st, v5,
+                     gradX ? &vo : nullptr);
+    if (rc) return rc;
+    return gradX ? launch_combine(gradX, gtmp, (size_t)A * M * D, out_scale, out_scale_dev, accumulate, st) : SKB_OK;
+}
+
+int skb_gram_weighted_sum(const double* G, int A, int B, int pairs, double w_diag, double w_off, double* acc, int accumulate,
+                          void* stream) {
+    if (A <= 0 || B <= 0) return SKB_ERR_BAD_SHAPE;
+    if (pairs != SKB_PAIRS_GRAM && pairs != SKB_PAIRS_BATCH && pairs != SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;
+    if (!G || !acc) return SKB_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) {
+        int rc = check_cuda(cudaMemsetAsync(acc, 0, sizeof(double), st));
+        if (rc) return rc;
+    }
+    const long n = pairs == SKB_PAIRS_BATCH ? (long)A : (long)A * B;
+    long blocks = (n + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    gram_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, n, pairs == SKB_PAIRS_BATCH ? 0 : B, w_diag, w_off, acc);
+    return check_launch();
 }
 
 int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,

@@ -241,7 +241,7 @@ bool fwd5_scaled_exp(int M, int logd, int D) {
     const int nw = fwd5_plan(M, logd, &rcp, &lpp);
     if (nw != 1) return false;
     const int dp2 = padded_dim(D) / 2, R = rcp << logd;
-    return rcp * dp2 <= ((lpp == 16 && R > 8) ? 12 : 8);
+    return R > 8 && rcp * dp2 <= ((lpp == 16 && R > 8) ? 12 : 8);
 }
 
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
@@ -286,6 +286,111 @@ int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     if (mode == 1) return rbf ? launch_group_adj5_rbf_store(rcp, logd, args.Dp / 2, args, st) : launch_group_adj5_lin_store(rcp, logd, args.Dp / 2, args, st);
     if (mode == 3) return rbf ? launch_group_adj5_rbf_rev(rcp, logd, args.Dp / 2, args, st) : launch_group_adj5_lin_rev(rcp, logd, args.Dp / 2, args, st);
     return SKB_ERR_UNSUPPORTED;
+}
+
+// ---- adjoint by reconstruction ---------------------------------------------------------------------------------
+static int g_adjoint_mode = -1;
+void set_adjoint_mode(int mode) { g_adjoint_mode = mode; }
+int get_adjoint_mode() { return g_adjoint_mode; }
+
+static int pow2_ceil(int v) {
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+
+// warps per pair (1, 2, 4; 0 = not covered), coarse rows per lane and lanes per pair of the reconstruction kernels:
+// SKB_RECON5_*_SHAPES of skb_recon5_launch.cuh (strips of at most 8 fine rows)
+static int recon5_plan(int M, int logd, int* rc_out, int* lpp_out) {
+    if (logd > 3) return 0;
+    const int rmax = 8 >> logd;
+    if (g_adjoint_mode != 1) {
+        const int rc = pow2_ceil((M + 15) / 16);
+        if (rc <= rmax && (rc << logd) >= 4) {
+            *rc_out = rc; *lpp_out = 16;
+            return 1;
+        }
+    }
+    *lpp_out = 32;
+    {
+        const int rc = pow2_ceil((M + 31) / 32);
+        if (rc <= rmax) {
+            *rc_out = rc;
+            return 1;
+        }
+    }
+    if (logd <= 2) {
+        for (int nw = 2; nw <= 4; nw *= 2)
+            if (M <= 32 * nw * rmax) {
+                *rc_out = rmax;
+                return nw;
+            }
+    }
+    return 0;
+}
+
+bool recon5_applies(int kind, int M, int N, int D, int logd, bool s1) {
+    if (g_adjoint_mode == 0 || s1 || N < 4) return false;
+    if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
+    const int Dp = padded_dim(D);
+    if (Dp != 4 && Dp != 6 && Dp != 10) return false;
+    int rc, lpp;
+    return recon5_plan(M, logd, &rc, &lpp) > 0;
+}
+
+int launch_recon5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
+    int rc = 0, lpp = 32;
+    const int nw = recon5_plan(args.M, logd, &rc, &lpp);
+    if (nw == 0) return SKB_ERR_UNSUPPORTED;
+    fill_v5_constants(args, logd);
+    if (!args.counter) return SKB_ERR_WORKSPACE;
+    int err = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
+    if (err) return err;
+    const bool rbf = kind == KIND_RBF;
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_start, st);
+    if (nw > 1) err = rbf ? launch_group_recon5_rbf_nw(mode, rc, logd, args.Dp / 2, nw, args, st) : launch_group_recon5_lin_nw(mode, rc, logd, args.Dp / 2, nw, args, st);
+    else if (lpp == 16) err = rbf ? launch_group_recon5_rbf_l16(mode, rc, logd, args.Dp / 2, 1, args, st) : launch_group_recon5_lin_l16(mode, rc, logd, args.Dp / 2, 1, args, st);
+    else err = rbf ? launch_group_recon5_rbf_l32(mode, rc, logd, args.Dp / 2, 1, args, st) : launch_group_recon5_lin_l32(mode, rc, logd, args.Dp / 2, 1, args, st);
+    if (g_ev_start && g_ev_stop) cudaEventRecord(g_ev_stop, st);
+    return err;
+}
+
+__global__ void vjp_accumulate_kernel(const double* __restrict__ gp, long job0, long njobs, int A, int B, int M, int D, int pairs,
+                                      const double* __restrict__ gout, double w_diag, double w_off, double* __restrict__ gradX,
+                                      const unsigned int* cond) {
+    if (cond != nullptr && *cond == 0u) return;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)M * D;
+    if (idx >= njobs * per) return;
+    const long jl = idx / per;
+    const long md = idx - jl * per;
+    const long pi = job0 + jl;
+    const long a = pairs == PAIRS_BATCH ? pi : pi / B;
+    const long b = pairs == PAIRS_BATCH ? pi : pi - a * B;
+    const double coef = gout ? gout[pi] : (a == b ? w_diag : w_off);
+    (void)A;
+    atomicAdd(gradX + a * per + md, coef * gp[idx]);
+}
+
+int launch_vjp_accumulate(const double* gp, long job0, long njobs, int A, int B, int M, int D, int pairs, const double* gout,
+                          double w_diag, double w_off, double* gradX, const unsigned int* cond, cudaStream_t st) {
+    const long n = njobs * (long)M * D;
+    if (n == 0) return SKB_OK;
+    vjp_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gp, job0, njobs, A, B, M, D, pairs, gout, w_diag, w_off, gradX, cond);
+    return check_launch();
+}
+
+__global__ void cond_zero_kernel(double* __restrict__ ptr, size_t n, const unsigned int* cond) {
+    if (cond != nullptr && *cond == 0u) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) ptr[i] = 0.0;
+}
+
+int launch_cond_zero(double* ptr, size_t n, const unsigned int* cond, cudaStream_t st) {
+    if (n == 0) return SKB_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 2048) blocks = 2048;
+    cond_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>(ptr, n, cond);
+    return check_launch();
 }
 
 int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {

@@ -138,17 +138,31 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //                   sigkernel.py:438-469), multiplied cell by cell with the stored forward grid (read one step
 //                   ahead), reduced to coarse sensitivities S and contracted with the analytic static-kernel
 //                   derivative into per-point gradients (sigkernel.py:470-500), see solver_kernel
+// MODE_FWD_EMIT     forward that also leaves the LAST ROW and the LAST COLUMN of every pair's grid (KArgs.brow /
+//                   .bcol): all the adjoint pass below needs from the forward solve
+// MODE_REV_RECON    adjoint pass WITHOUT a stored grid: the reversed sweep carries a second stencil that rebuilds the
+//                   forward solution backwards from its last row / column, u00 = (a (u10 + u01) - u11) / b -- the same
+//                   3-instruction update with coefficients (a/b, -1/b), same neighbours, same sweep direction as the
+//                   reversed-path solve.  Zero grid traffic (the stored-grid pair moves 16 B per fine node through HBM:
+//                   4.2 GB per 128 x 128 Gram at len 64, dyadic order 1).  The backward recurrence amplifies rounding
+//                   errors by the growth of the solution squared, so every pair checks u[., 0] = 1 at the end of its
+//                   sweep and raises KArgs.flag when it misses by more than recon_tol: the host side has already queued
+//                   the stored-grid kernels behind a device-side test of that flag (KArgs.cond).  The epilogue can
+//                   contract the per-point gradients with d loss / d K on the fly (gradX += coef * grad_points, atomic).
 // LPP = lanes per pair: 32 (default), or 16 -- then a warp carries TWO independent pair streams (lanes 0-15 and
 // 16-31), each lane owns twice the rows and the per-step overhead is spread over twice the cells.
 template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0, int LPP = 32>
 __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
-    static_assert(LPP == 32 || (LPP == 16 && NW == 1 && MODE == 0), "16 lanes per pair: forward only, one warp");
+    static_assert(LPP == 32 || (LPP == 16 && NW == 1 && (MODE == 0 || MODE == MODE_FWD_EMIT || MODE == MODE_REV_RECON)),
+                  "16 lanes per pair: one warp; forward, forward + boundaries, reconstruction adjoint");
     constexpr int NSTR = 32 / LPP;               // pair streams per warp
     constexpr int F = 1 << LOGD;
     constexpr int R = RC * F;
     constexpr bool STORE = MODE == MODE_FWD_STORE, REVG = MODE == MODE_REV_GRAD;
-    static_assert(MODE == 0 || STORE || REVG, "unknown mode");
-    static_assert(MODE == 0 || (NW == 1 && LOGD >= 1), "the adjoint modes use one warp per pair and 16-byte grid rows");
+    constexpr bool EMIT = MODE == MODE_FWD_EMIT, RECON = MODE == MODE_REV_RECON;
+    constexpr bool REVX = REVG || RECON;          // reversed sweep: sensitivities, gradient epilogue
+    static_assert(MODE == 0 || STORE || REVG || EMIT || RECON, "unknown mode");
+    static_assert(!(STORE || REVG) || (NW == 1 && LOGD >= 1), "the stored-grid modes use one warp per pair and 16-byte grid rows");
     // REV_GRAD reads the stored grid through a per-lane cp.async ring in shared memory, DEPTH steps ahead (the
     // lane-major layout makes every lane's stream contiguous): the loads of a whole DEPTH-step window are in
     // flight per lane, which is what it takes to cover the loaded HBM latency (measured ~3 us) -- one step ahead
@@ -156,12 +170,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr bool STAGE = REVG && (F * R <= 32);
     constexpr int DEPTH = (F * R <= 8) ? 4 : (F * R <= 16 ? 2 : 1);
     constexpr int NP = F * R / 2;                // 16-byte pieces per lane and step
-    constexpr bool GREG = REVG && (RC * DP2 <= 6);   // gradient accumulators in registers instead of shared memory
+    constexpr bool GREG = REVX && (RC * DP2 <= 6);   // gradient accumulators in registers instead of shared memory
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= ((LPP == 16 && R > 8) ? 12 : 8));   // x rows of the pair in registers (the 16-row
                                                                            // strips run 8 warps per SM: room for 12 double2)
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
     constexpr int RING = 64;                     // job ring depth (lane 0 is < 32 NW steps = RING/2 wraps ahead)
+    if ((MODE == MODE_FWD_STORE || MODE == MODE_REV_GRAD) && p.cond != nullptr) {
+        // stored-grid passes queued as the fallback of the reconstruction adjoint: run only if it raised its flag
+        if (*reinterpret_cast<const volatile unsigned int*>(p.cond) == 0u) return;
+    }
     const int glane = threadIdx.x;               // position in the wavefront
     const int lane = glane & 31;
     const int wid = glane >> 5;
@@ -175,9 +193,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 
     constexpr int Fq = 1 << LOGD, Rq = RC * Fq;
     constexpr bool XREGq = (RC * DP2 <= ((LPP == 16 && Rq > 8) ? 12 : 8));
-    // pre-scaled exp argument + 2^11 table: single-warp forward variants whose x rows live in registers (with the x rows
-    // in shared memory the 16 KB table would cost a resident block per SM).  Keep in sync with fwd5_scaled_exp().
-    constexpr bool SCALED = MODE == 0 && NW == 1 && XREGq;
+    // pre-scaled exp argument + 2^11 table: single-warp forward variants with strips of more than 8 rows (8 resident
+    // blocks per SM: room for 16 KB each) whose x rows live in registers.  Keep in sync with fwd5_scaled_exp().
+    constexpr bool SCALED = (MODE == 0 || EMIT) && NW == 1 && XREGq && Rq > 8;
     constexpr int ETAB = SCALED ? EXP_TAB5 : EXP_TAB;
     __shared__ double etab[ETAB];                // RBF: kscale * 2^(j/ETAB)
     __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset, -) in bytes
@@ -193,6 +211,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int DXQ = (NL + 1) * 8;                       // byte stride of dx[q][slot]
     __shared__ double2 tx[3][H][NL + 1];
     __shared__ double dx[3][NL + 1];
+    // REV_RECON: the same exchange for the rebuilt forward solution, and the sensitivities of a lane's last coarse row
+    // (this and the previous column) going down one lane
+    __shared__ double2 txr[RECON ? 3 : 1][RECON ? H : 1][RECON ? NL + 1 : 1];
+    __shared__ double2 sxr[RECON ? 3 : 1][RECON ? NL + 1 : 1];
     if (KIND == KIND_RBF) {
         for (int j = glane; j < ETAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / ETAB));
     }
@@ -215,6 +237,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             for (int q = 0; q < 3; ++q) {
                 for (int h = 0; h < H; ++h) tx[q][h][slot] = make_double2(1.0, 1.0);
                 dx[q][slot + LPP * (LPP == 32 ? NW : 1)] = 0.0;
+                if (RECON) {
+                    for (int h = 0; h < H; ++h) txr[RECON ? q : 0][RECON ? h : 0][RECON ? slot : 0] = make_double2(1.0, 1.0);
+                    sxr[RECON ? q : 0][RECON ? slot : 0] = make_double2(0.0, 0.0);
+                }
             }
             ring_s[sid][0] = make_int4(has_job ? first_job : -1, (int)xo, (int)yo, 0);
             job_next = has_job ? (int)(G + atomicAdd(p.counter, 1u)) : p.njobs;
@@ -240,12 +266,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     }
     const unsigned txb = (unsigned)__cvta_generic_to_shared(&tx[0][0][slot]);   // read slot; write slot = +16
     const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][slot]);      // write slot; read slot = +8
+    const unsigned txrb = RECON ? (unsigned)__cvta_generic_to_shared(&txr[0][0][RECON ? slot : 0]) : 0u;
+    const unsigned sxrb = RECON ? (unsigned)__cvta_generic_to_shared(&sxr[0][RECON ? slot : 0]) : 0u;
+    constexpr int SXQ = (NL + 1) * 16;                      // byte stride of sxr[q][slot]
 
     double2 xr[XREG ? RC : 1][DP2];
     // !XREG: the lane's rows are staged in shared memory once per pair ([piece][lane]: conflict-free 16-byte
     // accesses) and re-read every step from there -- global loads consumed in the step that issues them were the
     // reason the wide-row shapes (D + 1 = 10) ran latency-bound
-    constexpr bool XSM = !XREG && (RC * DP2 * 32 * NW * 16 <= 20480);   // (else: straight from global / L1 every step)
+    // (else: straight from global / L1 every step; the reconstruction adjoint has its own exchange arrays to fit in)
+    constexpr bool XSM = !XREG && (RC * DP2 * 32 * NW * 16 <= (RECON ? 10240 : 20480));
     __shared__ double2 xs_s[XSM ? RC * DP2 : 1][XSM ? 32 * NW : 1];
     const double* xrow[(XREG || XSM) ? 1 : RC];
     const double* yp = p.Yp;                      // y row of the NEXT production column
@@ -287,12 +317,68 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     for (int rc = 0; rc < (GREG ? RC : 1); ++rc)
 #pragma unroll
         for (int e2 = 0; e2 < (GREG ? Dp : 1); ++e2) ga[rc][e2] = 0.0;
+    constexpr int GL = 32 * NW;                   // lanes of the block: stride of the per-lane shared arrays
+    if (REVX) {
+        if (!GREG) for (int i = 0; i < RC * (D + 1); ++i) gacc[i * GL + glane] = 0.0;
+    }
     if (REVG) {
-        if (!GREG) for (int i = 0; i < RC * (D + 1); ++i) gacc[i * 32 + lane] = 0.0;
 #pragma unroll
         for (int f = 0; f < F; ++f)
 #pragma unroll
             for (int r = 0; r < R; ++r) fw[REVG ? f : 0][REVG ? r : 0] = 0.0;
+    }
+    // ---- REV_RECON: the rebuilt forward solution ub (reversed coordinates: ub(p', q') = u[MM - p', NN - q']) ----------
+    double ub[RECON ? R : 1], topsb[RECON ? F : 1], topprevb = 1.0, bpre[RECON ? F : 1];
+    double chk_tol = 0.0;                         // recon_tol * max(1, |k|) of the stencil stream's pair
+#pragma unroll
+    for (int r = 0; r < (RECON ? R : 1); ++r) ub[r] = 1.0;
+#pragma unroll
+    for (int f = 0; f < (RECON ? F : 1); ++f) { topsb[f] = 1.0; bpre[f] = 1.0; }
+    // boundary arrays of the stencil stream's pair (cbr: row reached through lane 0's top; set at the re-arm) and of the
+    // pair the production stream is in (nbr / nbc: fixed when the production column wraps, 4 steps before the re-arm)
+    const double* cbr = p.brow;
+    const double* nbr = p.brow;
+    const double* nbc = p.bcol;
+    // staging of a lane's first column u[., NN] (R + 1 values incl. the node above the strip, then u[MM, NN] = k itself,
+    // the scale of the boundary check): [k][lane] behind gacc
+    double* const bstg = RECON ? gacc + (GREG ? 0 : (size_t)RC * (D + 1) * GL) : nullptr;
+    auto pair_boundaries = [&](int job_) {
+        // slot of the pair in the forward launch's boundary arrays; under bsym the pair (a, b), a > b, reads the
+        // transposed grid of (b, a)
+        if (RECON) {
+            long sl = p.job0 + (job_ >= 0 ? job_ : 0);
+            bool swp = false;
+            if (p.bsym) {
+                int a, b;
+                job_decode(p, sl, a, b);
+                swp = a > b;
+                const long lo = swp ? b : a, hi = swp ? a : b;
+                sl = lo * p.A - lo * (lo - 1) / 2 + (hi - lo);
+            }
+            const double* br = p.brow + sl * p.brow_stride;
+            const double* bc = p.bcol + sl * p.bcol_stride;
+            nbr = swp ? bc : br;
+            nbc = swp ? br : bc;
+        }
+    };
+    auto stage_first_column = [&](bool real) {
+        if (RECON) {
+            // ub[r] = u[MM - pl R - r - 1, NN] (r = -1 .. R-1) = nbc[MM - pl R - R + k], k = 0 .. R
+            const long i0 = MMl - (long)(pl + 1) * R;
+#pragma unroll
+            for (int k = 0; k <= R + 1; ++k) {
+                const bool ok = real && (k > R || i0 + k >= 0);
+                const double* src = ok ? nbc + (k > R ? MMl : i0 + k) : p.bcol;
+                const int n8 = ok ? 8 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bstg + k * GL + glane)), "l"(src), "r"(n8) : "memory");
+            }
+            cp_async_commit();
+        }
+    };
+    if (RECON) {
+        // lane 0 of a pair starts inside its first pair (no production wrap before the first re-arm)
+        pair_boundaries(pjob);
+        stage_first_column(pjob >= 0);
     }
     // Layout of the stored grid (v5 adjoint): LANE-major, [job][forward lane t][fine column q][R rows] -- each
     // lane streams through its own contiguous NNf * R doubles, forwards when storing, backwards when the
@@ -400,20 +486,33 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         constexpr int Q = decltype(qc)::value;    // exchange buffer of this step
         // next step's stencil column is c+1: lane-1 needs this lane's first-row d[c+1] = dC as of NOW (made
         // one step ago), so this exchange does not wait for this step's production
-        sts_f64<Q * DXQ>(dxb, REVG ? klast[0] - dC[0] : dC[0]);
+        sts_f64<Q * DXQ>(dxb, REVX ? klast[0] - dC[0] : dC[0]);
+        if (RECON) {
+            // lane 0 of the pair: the rebuilt row above its strip is the forward solution's LAST ROW -- the values of
+            // the NEXT step are loaded now (a step of latency hiding) and replace what the exchange delivers
+            const bool wrapn = c == N - 1;
+            const int jn_ = wrapn ? pjob : sjob;
+            const int cn = wrapn ? 0 : c + 1;
+            const double* brn = wrapn ? nbr : cbr;
+            const bool okb = pl == 0 && jn_ >= 0 && cn < N - 1;
+#pragma unroll
+            for (int f = 0; f < (RECON ? F : 1); ++f) bpre[f] = okb ? __ldg(brn + (NNf - (long)cn * F - f - 1)) : 1.0;
+        }
         const bool real_col = sjob >= 0 && c < N - 1;
         if (REVG && !STAGE) load_fw(sjob, c);
         if (STAGE) stage_consume(sq);
         double kc[RC];                            // REV_GRAD: k at (own node rows, node column c)
         double up_c = 0.0, up_c1 = 0.0;           // REV_GRAD: S of lane-1's last coarse row at columns c, c-1
-        double sacc2[REVG ? RC : 1][REVG ? F : 1];
-        if (REVG) {
+        double sacc2[REVX ? RC : 1][REVX ? F : 1];
+        if (REVX) {
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) {
-                kc[rc] = dA[rc];                  // REV_GRAD keeps the k history itself (dA, dB, dC = k at columns c, c+1, c+2)
+                kc[rc] = dA[rc];                  // the reversed sweeps keep the k history itself (dA, dB, dC = k at columns c, c+1, c+2)
 #pragma unroll
-                for (int f = 0; f < F; ++f) sacc2[REVG ? rc : 0][REVG ? f : 0] = 0.0;
+                for (int f = 0; f < F; ++f) sacc2[REVX ? rc : 0][REVX ? f : 0] = 0.0;
             }
+        }
+        if (REVG) {
             up_c = shfl_up1(Slast_cur);
             up_c1 = shfl_up1(Slast_prev);
             if (lane == 0) { up_c = 0.0; up_c1 = 0.0; }
@@ -427,18 +526,50 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         for (int rc = 0; rc < RC; ++rc) {
             // REV_GRAD: the history holds k, so d[c] = k[c+1] - k[c] is formed here (same operands, same rounding
             // as in the other modes, where it is formed once at production time)
-            const double dlo = REVG ? dB[rc] - dA[rc] : dA[rc];
-            const double dhi = rc + 1 < RC ? (REVG ? dB[rc + 1 < RC ? rc + 1 : rc] - dA[rc + 1 < RC ? rc + 1 : rc] : dA[rc + 1 < RC ? rc + 1 : rc]) : dn;
+            const double dlo = REVX ? dB[rc] - dA[rc] : dA[rc];
+            const double dhi = rc + 1 < RC ? (REVX ? dB[rc + 1 < RC ? rc + 1 : rc] - dA[rc + 1 < RC ? rc + 1 : rc] : dA[rc + 1 < RC ? rc + 1 : rc]) : dn;
             const double el = dhi - dlo;
             cb[rc] = fma(el, el, -1.0);
             ca[rc] = fma(el, p.sqrt3, cb[rc] + 2.0);
         }
+        // REV_RECON: coefficients of the backward update u00 = (a/b)(u10 + u01) - (1/b) u11:  cib = -1/b = 1/cb, cia = -ca cib
+        double cia[RECON ? RC : 1], cib[RECON ? RC : 1];
+        if (RECON) {
+#pragma unroll
+            for (int rc = 0; rc < RC; ++rc) {
+                double r0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(cb[rc]));
+                double e0 = fma(-cb[rc], r0, 1.0);
+                r0 = fma(r0, e0, r0);
+                e0 = fma(-cb[rc], r0, 1.0);
+                r0 = fma(r0, e0, r0);
+                cib[RECON ? rc : 0] = r0;
+                cia[RECON ? rc : 0] = -(ca[rc] * r0);
+            }
+        }
 
         // ---- 2. the stencil: R rows x F fine columns in registers, anti-diagonal order ---------------
         double U[R][F];
+        double UB[RECON ? R : 1][RECON ? F : 1];
 #pragma unroll
         for (int dgl = 0; dgl < R + F - 1; ++dgl) {
             double ss[F], tt[F];
+            double ssb[RECON ? F : 1], ttb[RECON ? F : 1];
+            if (RECON) {
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    const int r = dgl - f;
+                    if (r >= 0 && r < R) {
+                        const int rm = r > 0 ? r - 1 : 0, fm = f > 0 ? f - 1 : 0;
+                        const double leftb = f == 0 ? ub[RECON ? r : 0] : UB[RECON ? r : 0][RECON ? fm : 0];
+                        const double upb = r == 0 ? topsb[RECON ? f : 0] : UB[RECON ? rm : 0][RECON ? f : 0];
+                        const double diagb = r == 0 ? (f == 0 ? topprevb : topsb[RECON ? fm : 0])
+                                                    : (f == 0 ? ub[RECON ? rm : 0] : UB[RECON ? rm : 0][RECON ? fm : 0]);
+                        ssb[RECON ? f : 0] = leftb + upb;
+                        ttb[RECON ? f : 0] = cib[RECON ? (r >> LOGD) : 0] * diagb;
+                    }
+                }
+            }
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const int r = dgl - f;
@@ -457,6 +588,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     const double diag = r == 0 ? (f == 0 ? topprev : tops[fm]) : (f == 0 ? u[rm] : U[rm][fm]);
                     tt[f] = cb[r >> LOGD] * diag;
                     if (REVG) sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0] = fma(fw[REVG ? f : 0][REVG ? r : 0], diag, sacc2[REVG ? (r >> LOGD) : 0][REVG ? f : 0]);
+                    if (RECON) {
+                        // the rebuilt forward value of this cell's far corner times the reversed solution at its near corner
+                        const double ubn = fma(cia[RECON ? (r >> LOGD) : 0], ssb[RECON ? f : 0], ttb[RECON ? f : 0]);
+                        UB[RECON ? r : 0][RECON ? f : 0] = ubn;
+                        sacc2[RECON ? (r >> LOGD) : 0][RECON ? f : 0] = fma(ubn, diag, sacc2[RECON ? (r >> LOGD) : 0][RECON ? f : 0]);
+                        if (r == R - 1 && ((f & 1) || f == F - 1)) {
+                            const int f0 = f & ~1;
+                            const double v0 = UB[RECON ? r : 0][RECON ? f0 : 0], v1 = UB[RECON ? r : 0][RECON ? f : 0];
+                            if (f0 == 0) sts_f64x2<Q * TXQ + 16>(txrb, v0, v1);
+                            if (f0 == 2) sts_f64x2<Q * TXQ + TXH + 16>(txrb, v0, v1);
+                            if (f0 == 4) sts_f64x2<Q * TXQ + 2 * TXH + 16>(txrb, v0, v1);
+                            if (f0 == 6) sts_f64x2<Q * TXQ + 3 * TXH + 16>(txrb, v0, v1);
+                        }
+                    }
                     if (STORE && (R % 4 == 0 ? (r & 3) == 3 : (r & 1))) {
                         // u[p, q] = the diagonal input of cell (p, q); a lane's rows of one fine column leave as whole
                         // 32-byte sectors (R % 4 == 0) or 16-byte pairs, as soon as the last of them is known
@@ -495,8 +640,44 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         topprev = tops[F - 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = U[r][F - 1];
+        if (RECON) {
+            topprevb = topsb[RECON ? F - 1 : 0];
+#pragma unroll
+            for (int r = 0; r < R; ++r) ub[RECON ? r : 0] = UB[RECON ? r : 0][RECON ? F - 1 : 0];
+        }
+        if (EMIT) {
+            // the lane that owns grid row MM-1 leaves u[MM, c F + 1 ..] (the last row of the grid) behind
+            if ((unsigned)orc < (unsigned)RC && real_col) {
+                double* br = p.brow + (p.job0 + sjob) * p.brow_stride + 1 + (long)c * F;
+#pragma unroll
+                for (int rc = 0; rc < RC; ++rc)
+                    if (rc == orc) {
+#pragma unroll
+                        for (int f = 0; f < F; ++f) br[f] = U[(rc + 1) * F - 1][f];
+                    }
+                if (c == 0) br[-1] = 1.0;
+            }
+        }
         if (NW > 1) __syncthreads(); else __syncwarp();
         dn = lds_f64<Q * DXQ + 8>(dxb);
+        if (RECON) {
+            double vx, vy;
+            lds_f64x2<Q * TXQ>(txrb, vx, vy);
+            topsb[0] = vx;
+            if (F > 1) topsb[RECON && F > 1 ? 1 : 0] = vy;
+            if (F > 2) { lds_f64x2<Q * TXQ + TXH>(txrb, vx, vy); topsb[RECON && F > 2 ? 2 : 0] = vx; topsb[RECON && F > 3 ? 3 : 0] = vy; }
+            if (F > 4) {
+                lds_f64x2<Q * TXQ + 2 * TXH>(txrb, vx, vy); topsb[RECON && F > 4 ? 4 : 0] = vx; topsb[RECON && F > 5 ? 5 : 0] = vy;
+                lds_f64x2<Q * TXQ + 3 * TXH>(txrb, vx, vy); topsb[RECON && F > 6 ? 6 : 0] = vx; topsb[RECON && F > 7 ? 7 : 0] = vy;
+            }
+            if (pl == 0) {
+#pragma unroll
+                for (int f = 0; f < (RECON ? F : 1); ++f) topsb[f] = bpre[f];
+            }
+            // sensitivities of lane-1's last coarse row at the columns it finished in ITS previous step (= this lane's
+            // columns c and c-1): written after the barrier of that step, read after this one
+            lds_f64x2<((Q + 2) % 3) * SXQ>(sxrb, up_c, up_c1);
+        }
         {
             double vx, vy;
             lds_f64x2<Q * TXQ>(txb, vx, vy);
@@ -510,15 +691,15 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
 
         // ---- 2b. REV_GRAD: coarse sensitivities of column c -> second difference T -> W = T k -> accumulate ----
-        if (REVG) {
+        if (REVX) {
             const bool dummy = c >= N - 1;
             double Scur[RC];
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) {
-                double t = sacc2[REVG ? rc : 0][0];
+                double t = sacc2[REVX ? rc : 0][0];
 #pragma unroll
-                for (int f = 1; f < F; ++f) t += sacc2[REVG ? rc : 0][REVG ? f : 0];
-                const bool ok = !dummy && (lane * RC + rc < M - 1);
+                for (int f = 1; f < F; ++f) t += sacc2[REVX ? rc : 0][REVX ? f : 0];
+                const bool ok = !dummy && (pl * RC + rc < M - 1);
                 Scur[rc] = ok ? t * p.scale4 : 0.0;
             }
 #pragma unroll
@@ -536,15 +717,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = fma(W, yv.y, ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0]);
                     }
                 } else {
-                    double* acc = gacc + (rc * (D + 1)) * 32 + lane;
+                    double* acc = gacc + (rc * (D + 1)) * GL + glane;
                     acc[0] += W;
-                    for (int k = 0; k < D; ++k) acc[(k + 1) * 32] = fma(W, __ldg(syp + 1 + k), acc[(k + 1) * 32]);
+                    for (int k = 0; k < D; ++k) acc[(k + 1) * GL] = fma(W, __ldg(syp + 1 + k), acc[(k + 1) * GL]);
                 }
             }
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) Sprev[rc] = Scur[rc];
             Slast_prev = Slast_cur;
             Slast_cur = Scur[RC - 1];
+            if (RECON) sts_f64x2<Q * SXQ + 16>(sxrb, Slast_cur, Slast_prev);
             syp += Dp;
         }
 
@@ -560,7 +742,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
             if (KIND == KIND_RBF) acc = SCALED ? exp_scaled5(acc, etab, p) : exp_neg5(acc, etab, p);
-            dnew[rc] = REVG ? klast[rc] : acc - klast[rc];      // REV_GRAD: the history rotates k itself
+            dnew[rc] = REVX ? klast[rc] : acc - klast[rc];      // reversed sweeps: the history rotates k itself
             klast[rc] = acc;
         }
 
@@ -575,7 +757,24 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         ++c;
         yp += Dp;
         if (cc >= N - 2 || cc == pc) {
-            if (!REVG && cc == N - 2) {
+            if (EMIT && cc == N - 2 && sjob >= 0) {
+                // last coarse column done: this lane's part of the LAST COLUMN u[., NN] of the grid
+                double* bc = p.bcol + (p.job0 + sjob) * p.bcol_stride + 1 + (long)pl * R;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if ((long)pl * R + r < MMl) bc[r] = u[r];
+                if (pl == 0) bc[-1] = 1.0;
+            }
+            if (RECON && cc == N - 2 && sjob >= 0) {
+                // the rebuilt grid must end at the boundary u[., 0] = 1: a miss beyond recon_tol * max(1, |k|) (errors scale with
+                // the size of the solution; or a NaN) sends the whole call to the stored-grid kernels queued behind this one
+                bool bad = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if ((long)pl * R + r < MMl) bad = bad || !(fabs(ub[RECON ? r : 0] - 1.0) <= chk_tol);
+                if (bad) *p.flag = 1u;
+            }
+            if (!REVX && cc == N - 2) {
                 // last coarse column done: u[MM, NN] is in the lane that owns grid row MM-1
                 if (sjob >= 0 && (unsigned)orc < (unsigned)RC) {
                     double res = u[F - 1];
@@ -593,16 +792,26 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 }
             }
             if (cc == N - 1) {
-                if (REVG) {
+                if (REVX) {
                     // the pair is complete for this lane: emit its node rows (reversed order), clear the accumulators
                     const long pi = p.job0 + sjob;                      // GRAM: a * B + b; BATCH: a
+                    // REV_RECON: fused loss head -- d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
+                    double coef = 0.0;
+                    double* gx = nullptr;
+                    if (RECON && p.gradX != nullptr && sjob >= 0) {
+                        int a, b;
+                        job_decode(p, pi, a, b);
+                        coef = p.gout ? __ldg(p.gout + pi) : (a == b ? p.w_diag : p.w_off);
+                        gx = p.gradX + (long)a * M * D;
+                    }
                     const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + sxo);
 #pragma unroll
                     for (int rc = 0; rc < RC; ++rc) {
-                        const int np = lane * RC + rc;                  // reversed node row
-                        double* acc = gacc + (rc * (D + 1)) * 32 + lane;
+                        const int np = pl * RC + rc;                    // reversed node row
+                        double* acc = gacc + (rc * (D + 1)) * GL + glane;
                         if (sjob >= 0 && np < M) {
-                            double* gout = p.grad + (pi * M + (M - 1 - np)) * D;
+                            double* gout = p.grad ? p.grad + (pi * M + (M - 1 - np)) * D : nullptr;
+                            double* gxr = gx ? gx + (long)(M - 1 - np) * D : nullptr;
                             const double* xrw = sxb + (long)np * Dp;
                             if (GREG) {
                                 const double sW = ga[GREG ? rc : 0][0];
@@ -610,13 +819,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                 for (int k = 0; k < Dp - 1; ++k)
                                     if (k < D) {
                                         const double gy = ga[GREG ? rc : 0][GREG ? k + 1 : 0];
-                                        gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                        const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                        if (!RECON || gout) gout[k] = gv;
+                                        if (RECON && gxr) atomicAdd(gxr + k, coef * gv);
                                     }
                             } else {
                                 const double sW = acc[0];
                                 for (int k = 0; k < D; ++k) {
-                                    const double gy = acc[(k + 1) * 32];
-                                    gout[k] = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                    const double gy = acc[(k + 1) * GL];
+                                    const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                    if (!RECON || gout) gout[k] = gv;
+                                    if (RECON && gxr) atomicAdd(gxr + k, coef * gv);
                                 }
                             }
                         }
@@ -624,7 +837,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
                             for (int e2 = 0; e2 < (GREG ? Dp : 1); ++e2) ga[GREG ? rc : 0][e2] = 0.0;
                         } else {
-                            for (int k = 0; k <= D; ++k) acc[k * 32] = 0.0;
+                            for (int k = 0; k <= D; ++k) acc[k * GL] = 0.0;
                         }
                     }
                     sxo = xo; syo = yo;
@@ -635,6 +848,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) u[r] = 1.0;
                 topprev = 1.0;
+                if (RECON) {
+                    // first column of the rebuilt solution: u[., NN] of the pair the stencil stream moves on to (staged when
+                    // the production column wrapped), and that pair's last row for lane 0
+                    cp_async_wait<0>();
+                    topprevb = bstg[R * GL + glane];
+                    chk_tol = p.recon_tol * fmax(1.0, fabs(bstg[(R + 1) * GL + glane]));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) ub[RECON ? r : 0] = bstg[(R - 1 - r) * GL + glane];
+                    cbr = nbr;
+                }
                 c = 0;
                 sjob = pjob;
             }
@@ -663,6 +886,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 xo = (unsigned)ent.y;
                 yo = (unsigned)ent.z;
                 set_pair();                       // virtual / past the end: the same pair's data again
+                if (RECON) {
+                    pair_boundaries(pjob);
+                    stage_first_column(pjob >= 0);
+                }
             }
         }
 #pragma unroll

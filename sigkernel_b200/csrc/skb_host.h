@@ -37,6 +37,22 @@ struct KArgs {
     // the coefficient polynomial and of the table-driven exp live here so that they are constant-bank operands
     double kscale, sqrt3, inv_kscale;
     double ek, ehi, elo, e4, e3;
+    // adjoint by reconstruction (MODE_FWD_EMIT / MODE_REV_RECON of skb_fwd5.cuh): the forward pass leaves the last row
+    // and the last column of every pair's grid, brow[slot][k] = u[MM, k] (k = 0..NN) and bcol[slot][k] = u[k, NN]
+    // (k = 0..MM); the reversed sweep rebuilds the grid backwards from them.  slot = job index of the forward launch.
+    double* brow;
+    double* bcol;
+    long brow_stride, bcol_stride;   // doubles per pair (multiples of 4)
+    int bsym;                        // REV_RECON: the boundaries come from a PAIRS_SYM forward (slot of (a,b) = triangle
+                                     // index of (min, max); a > b reads the transposed grid: brow <-> bcol)
+    unsigned int* flag;              // REV_RECON: set to 1 if a rebuilt grid misses u[., 0] = 1 by more than recon_tol
+    double recon_tol;
+    const unsigned int* cond;        // if non-NULL the kernel returns at once unless *cond != 0 (stored-grid fallback)
+    // fused loss head of REV_RECON: gradX[a, m, :] += coef(a,b) * grad_points[a, b, m, :] (atomic), with
+    // coef = gout[pair] if gout, else (a == b ? w_diag : w_off)
+    const double* gout;
+    double* gradX;
+    double w_diag, w_off;
 };
 
 // records the cudaError_t for skb_last_cuda_error(); returns SKB_OK or SKB_ERR_CUDA
@@ -103,6 +119,28 @@ int launch_group_adj5_rbf_store(int rc, int logd, int dp2, const KArgs&, cudaStr
 int launch_group_adj5_rbf_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_adj5_lin_store(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 int launch_group_adj5_lin_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
+
+// ---- adjoint by reconstruction (MODE_FWD_EMIT / MODE_REV_RECON of skb_fwd5.cuh) ---------------------------------
+// development / tuning knob (process-wide): -1 = default (reconstruction, 16 lanes per pair when instantiated),
+// 0 = stored-grid kernels only, 1 = reconstruction with 32 lanes per pair only
+void set_adjoint_mode(int mode);
+int get_adjoint_mode();
+// true if the reconstruction kernels cover the problem (fused kind, scheme S2, len_y >= 4, strips of <= 8 fine rows on
+// up to 4 warps per pair: (len_x - 1) 2^d <= 1024 at dyadic order <= 2)
+bool recon5_applies(int kind, int M, int N, int D, int logd, bool s1);
+// mode: MODE_FWD_EMIT or MODE_REV_RECON; args as for launch_forward5 plus the boundary / loss-head fields
+int launch_recon5(int mode, int kind, int logd, KArgs args, cudaStream_t st);
+int launch_group_recon5_rbf_l16(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+int launch_group_recon5_rbf_l32(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+int launch_group_recon5_rbf_nw(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+int launch_group_recon5_lin_l16(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+int launch_group_recon5_lin_l32(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+int launch_group_recon5_lin_nw(int mode, int rc, int logd, int dp2, int nw, const KArgs&, cudaStream_t);
+// gradX[a, m, :] += coef(a, b) * gp[job - job0, m, :] for jobs [job0, job0 + njobs) (stored-grid fallback of the fused
+// loss head); zero n doubles; both only if *cond != 0 (cond may be NULL = always)
+int launch_vjp_accumulate(const double* gp, long job0, long njobs, int A, int B, int M, int D, int pairs, const double* gout,
+                          double w_diag, double w_off, double* gradX, const unsigned int* cond, cudaStream_t st);
+int launch_cond_zero(double* ptr, size_t n, const unsigned int* cond, cudaStream_t st);
 
 // ---- tile forward kernel (skb_tile.cuh): one pair per lane, one strip per warp, W-warp pipelines ---------------
 struct TArgs;

@@ -43,7 +43,7 @@
 
 namespace skb {
 
-constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3;
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5;
 
 // exp(x) for the RBF static kernel: x <= ~0 (|x - y|^2 >= 0 up to rounding), possibly hugely negative.
 // Table-driven: x = (256 n + j) ln2/256 + r, exp(x) = 2^n * T[j] * e^r with T[j] = 2^(j/256) in shared
@@ -95,6 +95,10 @@ __device__ __forceinline__ void job_decode(const KArgs& p, long j, int& a, int& 
 
 template <int MODE, int KIND, int RC, int LOGD, int DP2, bool EXACT, int MINB>
 __global__ void __launch_bounds__(32, MINB) solver_kernel(const KArgs p) {
+    if (MODE != MODE_FWD && p.cond != nullptr) {
+        // adjoint passes queued as the fallback of the reconstruction adjoint: run only if it raised its flag
+        if (*reinterpret_cast<const volatile unsigned int*>(p.cond) == 0u) return;
+    }
     constexpr int F = 1 << LOGD;   // fine columns per macro step
     constexpr int R = RC * F;      // fine rows per lane
     constexpr bool REV = (MODE == MODE_REV_S || MODE == MODE_REV_GRAD);

@@ -113,6 +113,86 @@ def sigkernel_forward_backward(X, Y, static_kind, static_param, dyadic_order, pa
     return out.view(A, B), gp.view(A, B, M, D)
 
 
+def adjoint_plan(M, N, D, dyadic_order, static_kind, naive=False):
+    """Kernel family the backward of this shape takes (include/sigkernel_b200.h: 6 = adjoint by reconstruction)."""
+    return lib.skb_adjoint_plan(int(M), int(N), int(D), int(dyadic_order), _STATIC[static_kind],
+                                _lib.SCHEME_S1 if naive else _lib.SCHEME_S2)
+
+
+def sigkernel_forward_ctx(X, Y, static_kind, static_param, dyadic_order, pairs="gram", naive=False):
+    """Forward values plus the boundary context the lazy backward needs (last row / column of every pair's grid).
+    Returns (k, ctx) or None when the shape is outside the reconstruction kernels (use sigkernel_forward_backward)."""
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    if adjoint_plan(M, N, D, dyadic_order, static_kind, naive) != 6:
+        return None
+    with torch.cuda.device(Xc.device):
+        out = torch.empty(_n_out(A, B, pairs), dtype=torch.float64, device=Xc.device)
+        cb = lib.skb_ctx_bytes(A, B, M, N, int(dyadic_order), _PAIRS[pairs])
+        ctx = torch.empty(cb, dtype=torch.uint8, device=Xc.device)
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
+        rc = lib.skb_sigkernel_fwd_ctx(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                       _STATIC[static_kind], float(static_param),
+                                       _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                       out.data_ptr(), ctx.data_ptr(), cb, ws.data_ptr(), nbytes, _stream())
+        if rc == -4:
+            return None
+        check(rc)
+    return (out if pairs == "batch" else out.view(A, B)), ctx
+
+
+def sigkernel_backward_vjp(X, Y, static_kind, static_param, dyadic_order, pairs, ctx, ctx_pairs, grad_out=None,
+                           w_diag=0.0, w_off=0.0, out_scale=1.0, out_scale_dev=None, into=None, want_points=False,
+                           naive=False):
+    """Reversed sweep over every ordered pair of `pairs` ('gram' / 'batch') contracted with d loss / d K on the fly:
+    gradX (A,M,D) fp64 = [into +] out_scale * [out_scale_dev] * sum_b coef(a,b) d k(X_a,Y_b)/d X_a, coef = grad_out[a,b]
+    or (w_diag on a == b, w_off elsewhere).  `ctx` comes from sigkernel_forward_ctx(..., ctx_pairs).  The (A,B,M,D)
+    tensor of the reference (sigkernel.py:405-416) is only materialised when want_points."""
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    with torch.cuda.device(Xc.device):
+        gradX = into if into is not None else torch.empty((A, M, D), dtype=torch.float64, device=Xc.device)
+        gp = torch.empty((_n_out(A, B, pairs), M, D), dtype=torch.float64, device=Xc.device) if want_points else None
+        go = None
+        if grad_out is not None:
+            go = grad_out.detach().to(torch.float64).contiguous()
+        osd = None
+        if out_scale_dev is not None:
+            osd = out_scale_dev.detach().to(torch.float64).contiguous()
+        ws, nbytes = _workspace(lib.skb_bwd_vjp_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
+        check(lib.skb_sigkernel_bwd_vjp(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                        _STATIC[static_kind], float(static_param),
+                                        _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                        ctx.data_ptr(), _PAIRS[ctx_pairs], go.data_ptr() if go is not None else None,
+                                        float(w_diag), float(w_off), float(out_scale),
+                                        osd.data_ptr() if osd is not None else None, 1 if into is not None else 0,
+                                        gradX.data_ptr(), gp.data_ptr() if gp is not None else None,
+                                        ws.data_ptr(), nbytes, _stream()))
+    if want_points:
+        return gradX, (gp if pairs == "batch" else gp.view(A, B, M, D))
+    return gradX
+
+
+def gram_weighted_sum(G, pairs, w_diag, w_off, acc=None):
+    """acc (1,) fp64 [+]= sum_{a,b} w(a,b) G[a,b] (w_diag on the diagonal / on every batch entry, w_off elsewhere)."""
+    Gc = G.detach()
+    if Gc.dtype != torch.float64 or not Gc.is_contiguous():
+        Gc = Gc.to(torch.float64).contiguous()
+    if pairs == "batch":
+        A, B = Gc.shape[0], Gc.shape[0]
+    else:
+        A, B = Gc.shape
+    with torch.cuda.device(Gc.device):
+        accumulate = acc is not None
+        if acc is None:
+            acc = torch.empty(1, dtype=torch.float64, device=Gc.device)
+        check(lib.skb_gram_weighted_sum(Gc.data_ptr(), A, B, _PAIRS[pairs], float(w_diag), float(w_off), acc.data_ptr(),
+                                        1 if accumulate else 0, _stream()))
+    return acc
+
+
 def sensitivity_from_static(Ks, dyadic_order, pairs="gram", naive=False):
     """Plugin path of the backward: (k, S) with S the coarse sensitivities (pairs, M-1, N-1)."""
     if not Ks.is_cuda:

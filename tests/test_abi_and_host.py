@@ -61,10 +61,24 @@ def test_workspace_sizes():
     assert lib.skb_fwd_workspace_bytes(0, 1, 4, 4, 2, 0, 0) == 0
     w = lib.skb_fwd_workspace_bytes(128, 128, 64, 64, 5, 2, 0)
     assert w >= 2 * 128 * 64 * 6 * 8 and w % 256 == 0
-    # backward: one padded forward grid per pair (row pitch 32 * rows-per-lane), capped at 8 GiB
+    # backward by reconstruction: prepared paths + the boundary context (last row and column of every grid: 2 * 128
+    # doubles per pair here) + at most 1 GiB of forward grids for the stored-grid fallback
     b = lib.skb_bwd_workspace_bytes(128, 128, 64, 64, 3, 1, 0)
-    assert 128 * 128 * 126 * 128 * 8 <= b <= 128 * 128 * 126 * 128 * 8 + (1 << 22)
-    assert lib.skb_bwd_workspace_bytes(512, 512, 128, 128, 8, 2, 0) <= (8 << 30) + (64 << 20)
+    ctx = lib.skb_ctx_bytes(128, 128, 64, 64, 1, 0)
+    assert ctx == 128 * 128 * 2 * 128 * 8
+    assert ctx + (1 << 30) - (1 << 22) <= b <= ctx + (1 << 30) + (1 << 22)
+    assert lib.skb_adjoint_plan(64, 64, 3, 1, 1, 0) == 6 and lib.skb_adjoint_plan(1000, 20, 2, 0, 0, 0) == 6
+    assert lib.skb_adjoint_plan(300, 40, 2, 1, 1, 0) == 6 and lib.skb_adjoint_plan(64, 64, 3, 1, 1, 1) == 1   # S1: stored grid
+    # stored-grid kernels only: one padded forward grid per pair (row pitch 32 * rows-per-lane), capped at 8 GiB
+    lib.skb_set_adjoint_mode(0)
+    try:
+        b = lib.skb_bwd_workspace_bytes(128, 128, 64, 64, 3, 1, 0)
+        assert 128 * 128 * 126 * 128 * 8 <= b <= 128 * 128 * 126 * 128 * 8 + (1 << 22)
+        assert lib.skb_bwd_workspace_bytes(512, 512, 128, 128, 8, 2, 0) <= (8 << 30) + (64 << 20)
+        assert lib.skb_adjoint_plan(64, 64, 3, 1, 1, 0) == 5
+    finally:
+        lib.skb_set_adjoint_mode(-1)
+    assert lib.skb_bwd_vjp_workspace_bytes(128, 128, 64, 64, 3, 1, 0) > 0
     assert lib.skb_bwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) == 0        # unsupported shape says so
     assert lib.skb_aux_workspace_bytes(2, 2, 8, 8, 1, 0) >= 4
     # shapes outside the register-resident kernels get the generic row-band workspace
@@ -176,9 +190,19 @@ def test_dispatch_plans_for_the_baseline_configs():
     assert lib.skb_forward_plan(1, 6, 2, 0, RBF, S2) == -1
     assert lib.skb_forward_plan(8, 6, 2, 0, 9, S2) == -2
     # backward
-    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S2) == 5      # cfg4
-    assert lib.skb_adjoint_plan(64, 64, 5, 2, RBF, S2) == 5
-    assert lib.skb_adjoint_plan(40, 70, 8, 0, RBF, S2) == 1      # dyadic order 0: v4 adjoint kernels
-    assert lib.skb_adjoint_plan(128, 128, 8, 2, RBF, S2) == 1    # more than one warp per pair: v4
-    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S1) == 1
-    assert lib.skb_adjoint_plan(1000, 6, 2, 0, RBF, S2) == -4    # backward not covered (SKB_ERR_UNSUPPORTED)
+    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S2) == 6      # cfg4: adjoint by reconstruction
+    assert lib.skb_adjoint_plan(64, 64, 5, 2, RBF, S2) == 6
+    assert lib.skb_adjoint_plan(40, 70, 8, 0, RBF, S2) == 6      # dyadic order 0 too
+    assert lib.skb_adjoint_plan(128, 128, 8, 2, RBF, S2) == 6    # two warps per pair
+    assert lib.skb_adjoint_plan(1000, 6, 2, 0, RBF, S2) == 6     # the reference's own limit: (len_x - 1) 2^d < 1024
+    assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S1) == 1      # _naive_solver: stored-grid v4 kernels
+    assert lib.skb_adjoint_plan(64, 3, 3, 1, RBF, S2) == 1       # len_y < 4
+    assert lib.skb_adjoint_plan(2000, 6, 2, 0, RBF, S2) == -4    # backward not covered (SKB_ERR_UNSUPPORTED)
+    assert lib.skb_adjoint_plan(300, 6, 2, 2, RBF, S2) == -4     # 1196 fine rows
+    lib.skb_set_adjoint_mode(0)
+    try:
+        assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S2) == 5      # stored grid on the v5 kernels
+        assert lib.skb_adjoint_plan(40, 70, 8, 0, RBF, S2) == 1      # dyadic order 0: v4 adjoint kernels
+        assert lib.skb_adjoint_plan(128, 128, 8, 2, RBF, S2) == 1    # more than one warp per pair: v4
+    finally:
+        lib.skb_set_adjoint_mode(-1)

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from tests._util import (FWD_TOL, GRAD_TOL_ANALYTIC, GRAD_TOL_REF, fwd_err, golden_names, grad_err, load_golden,
-                         make_paths)
+                         make_paths, static_of)
 
 pytestmark = pytest.mark.gpu
 
@@ -179,3 +179,202 @@ def test_cfg4_shape_properties(skb, O):
     wxx = (torch.ones(n, n, dtype=torch.float64, device="cuda") - torch.eye(n, dtype=torch.float64, device="cuda")) / (n * (n - 1.))
     expect = 2 * torch.einsum('ab,abmd->amd', wxx, gxx) + torch.einsum('ab,abmd->amd', torch.full_like(wxx, -2. / (n * n)), gp)
     assert grad_err(Xd.grad.cpu().numpy(), expect.cpu().numpy()) <= 1e-12
+
+
+# ---- adjoint by reconstruction (MODE_FWD_EMIT + MODE_REV_RECON), lazy fused backward, loss heads ------------------------
+@pytest.fixture()
+def stored_grid_only(skb):
+    skb._lib.lib.skb_set_adjoint_mode(0)
+    yield
+    skb._lib.lib.skb_set_adjoint_mode(-1)
+
+
+LONG = [
+    # A, B, M, N, D, d          two and four warps per pair, 16 and 32 lanes per pair, every dyadic order
+    (2, 2, 300, 12, 2, 1), (1, 2, 600, 9, 3, 0), (1, 1, 1000, 7, 2, 0), (2, 1, 130, 20, 8, 1), (1, 2, 256, 5, 5, 2),
+    (2, 2, 17, 6, 2, 3), (2, 2, 33, 40, 3, 2), (3, 2, 64, 64, 3, 1), (2, 2, 20, 9, 11 - 2, 0),
+]
+
+
+@pytest.mark.parametrize("A,B,M,N,D,d", LONG)
+@pytest.mark.parametrize("static", ["rbf", "linear"])
+def test_reconstruction_adjoint_vs_analytic_oracle(skb, O, A, B, M, N, D, d, static):
+    X = make_paths("bm", 500 + M, (A, M, D))
+    Y = make_paths("bm", 600 + N, (B, N, D))
+    ok = O.RBFKernel(1.1) if static == "rbf" else O.LinearKernel()
+    par = 1.1 if static == "rbf" else 1.0
+    assert skb.ops.adjoint_plan(M, N, D, d, static) == 6
+    Gref, gp_ref, _ = O.gram_grad_points_analytic(X, Y, ok, d)
+    G, gp = skb.ops.sigkernel_forward_backward(X.cuda(), Y.cuda(), static, par, d, "gram")
+    assert fwd_err(G.cpu().numpy(), Gref.numpy()) <= FWD_TOL
+    assert grad_err(gp.cpu().numpy(), gp_ref.numpy()) <= GRAD_TOL_ANALYTIC
+    # the lazy pair of entry points: same numbers, plus the fused contraction with an upstream gradient
+    res = skb.ops.sigkernel_forward_ctx(X.cuda(), Y.cuda(), static, par, d, "gram")
+    assert res is not None
+    G2, bctx = res
+    assert torch.equal(G2, G)
+    w = torch.linspace(-1.0, 2.0, A * B, dtype=torch.float64).reshape(A, B).cuda()
+    gx, gp2 = skb.ops.sigkernel_backward_vjp(X.cuda(), Y.cuda(), static, par, d, "gram", bctx, "gram", grad_out=w, want_points=True)
+    assert torch.equal(gp2, gp)
+    expect = torch.einsum('ab,abmd->amd', w, gp)
+    assert grad_err(gx.cpu().numpy(), expect.cpu().numpy()) <= 1e-12
+
+
+def test_reconstruction_agrees_with_the_stored_grid_kernels(skb):
+    X, Y = make_paths("rand", 81, (6, 40, 3)).cuda(), make_paths("rand", 82, (5, 33, 3)).cuda()
+    lib = skb._lib.lib
+    G1, gp1 = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, 1, "gram")
+    lib.skb_set_adjoint_mode(0)
+    try:
+        G0, gp0 = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, 1, "gram")
+    finally:
+        lib.skb_set_adjoint_mode(-1)
+    lib.skb_set_adjoint_mode(1)          # 32 lanes per pair
+    try:
+        G2, gp2 = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, 1, "gram")
+    finally:
+        lib.skb_set_adjoint_mode(-1)
+    assert fwd_err(G1.cpu().numpy(), G0.cpu().numpy()) <= 1e-12 and fwd_err(G2.cpu().numpy(), G0.cpu().numpy()) <= 1e-12
+    assert grad_err(gp1.cpu().numpy(), gp0.cpu().numpy()) <= 1e-10
+    assert grad_err(gp2.cpu().numpy(), gp0.cpu().numpy()) <= 1e-10
+
+
+def test_unstable_reconstruction_falls_back_to_the_stored_grid(skb, O):
+    """Increments large enough that the PDE solution grows by many orders of magnitude: rebuilding it backwards loses
+    all accuracy (growth squared), the boundary check raises the flag and the stored-grid kernels queued behind it take
+    over -- the result still matches the oracle; without the fallback room the flag is left for the caller."""
+    X = make_paths("rand", 91, (3, 40, 3)) * 3.0
+    Y = make_paths("rand", 92, (2, 40, 3)) * 3.0
+    Gref, gp_ref, _ = O.gram_grad_points_analytic(X, Y, O.LinearKernel(), 1)
+    assert float(Gref.abs().max()) > 1e8
+    G, gp = skb.ops.sigkernel_forward_backward(X.cuda(), Y.cuda(), "linear", 1.0, 1, "gram")
+    assert grad_err(G.cpu().numpy(), Gref.numpy()) <= 1e-10
+    assert grad_err(gp.cpu().numpy(), gp_ref.numpy()) <= GRAD_TOL_ANALYTIC
+    # fused loss head through the same fallback
+    res = skb.ops.sigkernel_forward_ctx(X.cuda(), Y.cuda(), "linear", 1.0, 1, "gram")
+    w = torch.linspace(0.5, 1.5, 6, dtype=torch.float64).reshape(3, 2)
+    gx = skb.ops.sigkernel_backward_vjp(X.cuda(), Y.cuda(), "linear", 1.0, 1, "gram", res[1], "gram", grad_out=w.cuda())
+    assert grad_err(gx.cpu().numpy(), O.gram_vjp(w, gp_ref).numpy()) <= GRAD_TOL_ANALYTIC
+    # a workspace without room for a forward grid: no fallback is queued, the flag word (byte 64) is set
+    lib, chk = skb._lib.lib, skb._lib.check
+    Xc, Yc = X.cuda(), Y.cuda()
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    Dp = 4
+    fixed = 256 + 2 * (((A * M * Dp * 8) + 255) // 256 * 256) + 2 * (((B * N * Dp * 8) + 255) // 256 * 256) + lib.skb_ctx_bytes(A, B, M, N, 1, 0)
+    ws = torch.zeros(fixed + 512, dtype=torch.uint8, device="cuda")
+    out = torch.empty(A * B, dtype=torch.float64, device="cuda")
+    gpo = torch.empty((A * B, M, D), dtype=torch.float64, device="cuda")
+    chk(lib.skb_sigkernel_fwd_bwd(Xc.data_ptr(), Yc.data_ptr(), 0, A, B, M, N, D, 1, 0, 1.0, 0, 0, out.data_ptr(), gpo.data_ptr(),
+                                  ws.data_ptr(), fixed + 512, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(ws[64:68].view(torch.int32).item()) == 1
+    # and a benign problem leaves it clear
+    Xs, Ys = (X / 3.0).cuda(), (Y / 3.0).cuda()
+    chk(lib.skb_sigkernel_fwd_bwd(Xs.data_ptr(), Ys.data_ptr(), 0, A, B, M, N, D, 1, 0, 1.0, 0, 0, out.data_ptr(), gpo.data_ptr(),
+                                  ws.data_ptr(), fixed + 512, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(ws[64:68].view(torch.int32).item()) == 0
+
+
+def test_symmetric_gram_with_gradients_solves_the_triangle_once(skb, O):
+    """compute_Gram(X, X, sym=True) with X.requires_grad: forward over a <= b only; the reversed sweep of (a, b), a > b,
+    reads the transposed grid of (b, a).  Same values and gradient as the full square; the reference doubles the
+    gradient because Y (= X) requires grad (sigkernel.py:410-412)."""
+    X = make_paths("rand", 95, (7, 21, 3))
+    w = torch.rand(7, 7, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    w = 0.5 * (w + w.T)
+    sk = skb.SigKernel(skb.RBFKernel(0.5), 1)
+    Xs = X.cuda().requires_grad_(True)
+    Gs = sk.compute_Gram(Xs, Xs, sym=True)
+    (Gs * w.cuda()).sum().backward()
+    Xf = X.cuda().requires_grad_(True)
+    Gf = sk.compute_Gram(Xf, Xf, sym=False)
+    (Gf * w.cuda()).sum().backward()
+    assert fwd_err(Gs.detach().cpu().numpy(), Gf.detach().cpu().numpy()) <= 1e-12
+    assert grad_err(Xs.grad.cpu().numpy(), Xf.grad.cpu().numpy()) <= 1e-11
+    _, gp_ref, _ = O.gram_grad_points_analytic(X, X, O.RBFKernel(0.5), 1)
+    assert grad_err(Xs.grad.cpu().numpy(), O.gram_vjp(w, gp_ref, y_requires_grad=True).numpy()) <= GRAD_TOL_ANALYTIC
+    # sym=True with two different tensors is NOT symmetric: it must not take the triangular shortcut
+    Y = make_paths("rand", 96, (7, 21, 3)).cuda()
+    G_bad = sk.compute_Gram(X.cuda(), Y, sym=True)
+    assert fwd_err(G_bad.cpu().numpy(), sk.compute_Gram(X.cuda(), Y).cpu().numpy()) <= 1e-13
+
+
+@pytest.mark.parametrize("which", ["mmd", "score", "distance"])
+def test_fused_loss_heads_match_the_composition(skb, O, which):
+    """compute_mmd / compute_scoring_rule / compute_distance through the fused loss head (_SigLoss) vs the reference's
+    composition of Grams evaluated with the oracle's analytic gradients."""
+    n, m = (6, 5) if which != "distance" else (6, 6)
+    X, Y = make_paths("rand", 101, (n, 18, 3)), make_paths("rand", 102, (m, 15, 3))
+    ok, d = O.RBFKernel(0.6), 1
+    sk = skb.SigKernel(skb.RBFKernel(0.6), d)
+    Xd = X.cuda().requires_grad_(True)
+    fn = {"mmd": sk.compute_mmd, "score": sk.compute_expected_scoring_rule, "distance": sk.compute_distance}[which]
+    loss = fn(Xd, Y.cuda())
+    assert loss.dim() == 0 and loss.grad_fn is not None and "SigLoss" in type(loss.grad_fn).__name__
+    (3.0 * loss).backward()
+    if which == "distance":
+        kxx, gxx, _ = O.batch_grad_points_analytic(X, X, ok, d)
+        kyy = O.compute_kernel(Y, Y, ok, d)
+        kxy, gxy, _ = O.batch_grad_points_analytic(X, Y, ok, d)
+        ref = kxx.mean() + kyy.mean() - 2 * kxy.mean()
+        gref = 3.0 * (gxx / n - 2.0 * gxy / n)
+    else:
+        Gxx, gxx, _ = O.gram_grad_points_analytic(X, X, ok, d)
+        Gxy, gxy, _ = O.gram_grad_points_analytic(X, Y, ok, d)
+        wxx = (torch.ones(n, n, dtype=torch.float64) - torch.eye(n, dtype=torch.float64)) / (n * (n - 1.))
+        wxy = torch.full((n, m), -2. / (n * m), dtype=torch.float64)
+        ref = O._offdiag_mean(Gxx) - 2. * Gxy.mean()
+        if which == "mmd":
+            ref = ref + O._offdiag_mean(O.compute_Gram(Y, Y, ok, d))
+        gref = 3.0 * (O.gram_vjp(wxx, gxx, True) + O.gram_vjp(wxy, gxy, False))
+    assert abs(float(loss.detach()) - float(ref)) <= 1e-11 * (abs(float(ref)) + 1)
+    assert grad_err(Xd.grad.cpu().numpy(), gref.numpy()) <= GRAD_TOL_ANALYTIC
+    # no-grad evaluation takes the same head and returns the same number
+    with torch.no_grad():
+        assert abs(float(fn(Xd, Y.cuda())) - float(loss.detach())) <= 1e-13
+
+
+def test_grad_mode_and_y_only_requires_grad(skb):
+    """(ADVICE r1) Only Y requires grad: the reference returns no gradient for Y, and nothing here may crash;
+    torch.no_grad() computes no backward work and returns tensors that do not require grad."""
+    sk = skb.SigKernel(skb.RBFKernel(0.5), 1)
+    X = make_paths("rand", 111, (3, 9, 2)).cuda()
+    Y = make_paths("rand", 112, (4, 7, 2)).cuda().requires_grad_(True)
+    G = sk.compute_Gram(X, Y)
+    G.sum().backward()
+    assert Y.grad is None
+    K = sk.compute_kernel(X, Y[:3])
+    K.sum().backward()
+    assert Y.grad is None
+    Xg = X.clone().requires_grad_(True)
+    with torch.no_grad():
+        G0 = sk.compute_Gram(Xg, Y.detach())
+    assert not G0.requires_grad
+    assert fwd_err(G0.cpu().numpy(), G.detach().cpu().numpy()) <= 1e-13
+
+
+def test_function_space_kernels_vs_oracle_and_gradient_flow(skb, O):
+    """RBF_ID / Linear_ID / RBF_CEXP (reference static_kernels.py:75-206): 4-D paths go through a host-side transform and
+    the fused kernels; values vs the oracle fed the same kernels, gradients flow back through the transform."""
+    X = make_paths("rand", 121, (3, 9, 4, 2))
+    Y = make_paths("rand", 122, (4, 7, 4, 2))
+    for mk, mo in ((skb.RBF_ID_Kernel(2.0), O.RBF_ID_Kernel(2.0)), (skb.Linear_ID_Kernel(), O.Linear_ID_Kernel()),
+                   (skb.RBF_CEXP_Kernel(1.0, 2.0, 4), O.RBF_CEXP_Kernel(1.0, 2.0, 4))):
+        ref = O.compute_Gram(X, Y, mo, 1).numpy()
+        got = skb.SigKernel(mk, 1).compute_Gram(X.cuda(), Y.cuda())
+        assert fwd_err(got.cpu().numpy(), ref) <= FWD_TOL
+        kref = O.compute_kernel(X, Y[:3], mo, 0).numpy()
+        kgot = skb.SigKernel(mk, 0).compute_kernel(X.cuda(), Y[:3].cuda())
+        assert fwd_err(kgot.cpu().numpy(), kref) <= FWD_TOL
+        # gradient w.r.t. the 4-D input = gradient w.r.t. the transformed paths pulled back through the transform
+        Xd = X.cuda().requires_grad_(True)
+        skb.SigKernel(mk, 1).compute_Gram(Xd, Y.cuda()).sum().backward()
+        Xt = mo.transform(X).detach().requires_grad_(True)
+        _, gp_ref, _ = O.gram_grad_points_analytic(Xt.detach(), mo.transform(Y), O.RBFKernel(mo.sigma) if hasattr(mo, "sigma") else O.LinearKernel(), 1)
+        gt = gp_ref.sum(dim=1)
+        Xc = X.clone().requires_grad_(True)
+        (mo.transform(Xc) * gt).sum().backward()
+        assert Xd.grad.shape == X.shape
+        assert grad_err(Xd.grad.cpu().numpy(), Xc.grad.numpy()) <= GRAD_TOL_ANALYTIC
