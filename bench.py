@@ -6,8 +6,10 @@
 
 Workload = BASELINE.json configs[2] (the headline): compute_Gram 128x128, len 64, dim 5, dyadic_order 2,
 RBFKernel(sigma=0.5), fp64, synthetic torch.rand paths (README recipe of the reference).  A step is one
-pass of the hot path over one batch: the whole Gram matrix.  At N>1 the X batch axis is sharded (weak
-scaling: every rank owns 128 rows of X, Y is replicated, one NCCL all-gather reassembles G).
+pass of the hot path over one batch: the whole Gram matrix, through the public API (SigKernel.compute_Gram; at
+N>1 sigkernel_b200.distributed.compute_Gram_sharded: weak scaling, every rank owns 128 rows of X, Y is
+replicated, G is reassembled on every rank).  Sub-objects of the same JSON line: `cfg4` (configs[3]:
+compute_mmd + backward, N=1) and `cfg5_sharded` (configs[4]: 512x512 sharded over the N ranks, N>1).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
 """
@@ -104,14 +106,29 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # the reference arm and the CPU baseline: the reference's own CPU algorithm on the host cores
 # ----------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _have_reference_package():
+    return os.path.isdir(os.path.join(REF_DIR, "sigkernel"))
+
+
 def _cpu_gram_rows(args):
-    """One worker: Gram rows [lo, hi) of the workload through the oracle (the reference's compiled
-    Cython solver when oracle/_ref is present, else the C restatement)."""
-    lo, hi, rank_seed = args
+    """One worker: Gram rows [lo, hi) of the workload on the CPU.  With the reference installed under baseline/_ref
+    (pip install --target) this is the UNMODIFIED reference through its own public API,
+    sigkernel.SigKernel(RBFKernel(0.5), 2).compute_Gram(X[lo:hi], Y); otherwise the oracle port around the reference's
+    compiled Cython solver (oracle/_ref) or the C restatement."""
+    lo, hi, rank_seed, threads = args
     import torch
-    torch.set_num_threads(1)
-    from oracle import sigkernel_oracle as O
+    torch.set_num_threads(threads)
     X, Y = make_inputs(rank_seed, torch)
+    if _have_reference_package():
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import sigkernel as ref
+        sk = ref.SigKernel(ref.RBFKernel(sigma=CFG["sigma"]), CFG["d"])
+        return float(sk.compute_Gram(X[lo:hi], Y).sum())
+    from oracle import sigkernel_oracle as O
     backend = "ref" if O.ref_backend() is not None else "c"
     out = []
     for r0 in range(lo, hi, 4):                       # 4 rows x 128 columns at a time: ~0.5 GB of grids
@@ -120,13 +137,23 @@ def _cpu_gram_rows(args):
     return torch.cat(out).sum().item()
 
 
-def cpu_gram_throughput(rows, workers):
-    """pairs/s of the CPU path on `rows` rows of X (x all 128 columns) using `workers` processes."""
-    import multiprocessing as mp
+def cpu_path_description():
+    if _have_reference_package():
+        return "reference", ("unmodified reference package (baseline/_ref) through its public API "
+                             "SigKernel(RBFKernel(0.5), 2).compute_Gram on CPU tensors")
     from oracle import sigkernel_oracle as O
-    kind = "reference" if O.ref_backend() is not None else "port"
+    if O.ref_backend() is not None:
+        return "reference-solver+port", "reference Cython solver (oracle/_ref) behind the oracle's torch port of the static kernel and tile()"
+    return "port", "oracle port (C restatement of the solver)"
+
+
+def cpu_gram_throughput(rows, workers, threads=1):
+    """pairs/s of the CPU path on `rows` rows of X (x all 128 columns) using `workers` processes of `threads` torch
+    threads each (the reference's PDE solve is single-threaded; only its static-kernel ops use torch threads)."""
+    import multiprocessing as mp
+    kind, _ = cpu_path_description()
     workers = max(1, min(workers, rows))
-    bounds = [(rows * w // workers, rows * (w + 1) // workers, 0) for w in range(workers)]
+    bounds = [(rows * w // workers, rows * (w + 1) // workers, 0, threads) for w in range(workers)]
     t0 = time.perf_counter()
     if workers == 1:
         _cpu_gram_rows(bounds[0])
@@ -149,23 +176,32 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    # bound the sample: ~2 rows per core (a row = 128 pairs ~ 0.2 s of one core), at most the full 128 rows
-    rows = min(CFG["A"], max(8, 8 * cores))
+    if _have_reference_package():
+        # import the reference (numba, sklearn, scipy ...: seconds) once, before the worker processes are forked
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import sigkernel  # noqa: F401
+    # bound the sample: one probe step with one row of X (128 pairs) per worker process sizes the timed steps to ~3 s each
+    # (the stock reference runs at a few hundred pairs/s per core: static kernel + tile() + single-threaded Cython solve)
+    workers = max(1, min(cores, 32))
+    _, t_probe, _, _ = cpu_gram_throughput(workers, workers)
+    rows = min(CFG["A"], workers * max(1, min(8, int(3.0 / max(t_probe, 1e-3)))))
     times = []
     for i in range(args.warmup + args.steps):
-        v, dt, kind, workers = cpu_gram_throughput(rows, cores)
+        v, dt, kind, workers = cpu_gram_throughput(rows, workers)
         if i >= args.warmup:
             times.append(dt)
     t = sum(times) / len(times)
     value = rows * CFG["B"] / t
+    _, how = cpu_path_description()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{rows} rows of X x 128 columns = {rows * CFG['B']} pairs per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
-                         "sample": f"{rows}x128 pairs per step, {workers} processes (one row block each), "
-                                   "static kernel + tile + Cython/C solve exactly as the reference's CPU branch"},
+                         "sample": f"{rows}x128 pairs per step; {how}; {workers} worker processes (one row block each, "
+                                   "1 torch thread each: the reference itself has no multi-core path for the solve)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,6 +231,106 @@ def measure_fp64_peak(skb, torch):
     return rates
 
 
+def _time_steps(torch, fn, steps, flush, barrier):
+    """CUDA-event time of `steps` calls of fn, L2 flushed before each; returns total ms (this rank)."""
+    total = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return total
+
+
+def bench_cfg4(skb, torch, dev, flush, steps, peak_rate):
+    """BASELINE configs[3]: compute_mmd + .backward(), batch 128, len 64, dim 3, dyadic_order 1, RBF, through the public API
+    (fused loss head: 3 forward solves, 2 reversed sweeps that rebuild the forward grid instead of reading a stored one)."""
+    A, L, D, d = 128, 64, 3, 1
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand((A, L, D), dtype=torch.float64, generator=g).to(dev)
+    Y = torch.rand((A, L, D), dtype=torch.float64, generator=g).to(dev)
+    sk = skb.SigKernel(skb.RBFKernel(0.5), d)
+    grads = []
+
+    def step():
+        Xg = X.detach().requires_grad_(True)
+        sk.compute_mmd(Xg, Y).backward()
+        grads.append(Xg.grad)
+        del grads[:-1]
+
+    for _ in range(3):
+        step()
+    ms = _time_steps(torch, step, steps, flush, None) / steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    G, gp = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, d, "gram")
+    e1.record()
+    torch.cuda.synchronize()
+    # one Gram with per-point gradients (the reference's eager grad_points), timed over a few calls
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        e0.record()
+        skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, d, "gram")
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    MM = (L - 1) << d
+    cells = A * A * MM * MM
+    # algorithmic DP instructions (SURVEY 8(d)): 4 per fine cell per sweep; the backward adds one sweep and ~2 per cell for
+    # the product with the forward grid: forward of K_XX, K_XY (full) and K_YY (triangle), reversed sweeps of K_XX, K_XY
+    dp = 4.0 * cells * 2.5 + 6.0 * cells * 2
+    ctx_bytes = 2 * A * A * 2 * (MM + 1) * 8          # last row + last column of every grid, two Grams, written once
+    return {"workload": "compute_mmd + backward batch=128 len=64 dim=3 dyadic_order=1 RBFKernel(0.5) fp64 (BASELINE.json configs[3])",
+            "ms_per_step": ms, "gram_with_grad_points_ms": min(ts),
+            "mmd_grad_finite": bool(torch.isfinite(grads[-1]).all().item()),
+            "hbm_GB_moved": (2 * ctx_bytes + 3 * A * A * 8 + 4 * A * L * D * 8) / 1e9,
+            "hbm_note": "algorithmic: boundary context written by the two forward solves and read by the two reversed sweeps, the "
+                        "three Gram matrices, paths and gradient; the stored-grid kernels of round 1 moved 8.4 GB here",
+            "roofline": {"bound": "fp64", "achieved": dp / (ms * 1e-3) / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
+                         "frac": dp / (ms * 1e-3) / peak_rate,
+                         "formula": "(4 * 2.5 + 6 * 2) * A*B*MM*NN / t / peak  (SURVEY.md 8(d))"}}
+
+
+def bench_cfg5(skb, torch, dist, dev, world, rank, flush, steps):
+    """BASELINE configs[4]: compute_Gram 512x512, len 128, dim 8, dyadic_order 2, RBF, strong-scaled over the ranks with
+    sigkernel_b200.distributed.compute_Gram_sharded; the leading block is checked against the reference fixture."""
+    A, L, D, d = 512, 128, 8, 2
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand((A, L, D), dtype=torch.float64, generator=g).to(dev)
+    Y = torch.rand((A, L, D), dtype=torch.float64, generator=g).to(dev)
+    sk = skb.SigKernel(skb.RBFKernel(0.5), d)
+    out = []
+
+    def step():
+        out.append(skb.distributed.compute_Gram_sharded(sk, X, Y))
+        del out[:-1]
+
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = _time_steps(torch, step, steps, flush, None)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    err = None
+    fix = os.path.join(ROOT, "tests", "golden", "cfg5_gram_rbf.npz")
+    if rank == 0 and os.path.exists(fix):
+        import numpy as np
+        z = np.load(fix, allow_pickle=False)
+        n = z["G"].shape[0]
+        got = out[-1][:n, :n].cpu().numpy()
+        err = float(np.max(np.abs(got - z["G"]) / (np.abs(z["G"]) + 1.0)))
+    return {"workload": "compute_Gram 512x512 len=128 dim=8 dyadic_order=2 RBFKernel(0.5) fp64 (BASELINE.json configs[4]), "
+                        f"rows of X sharded over {world} ranks, strong scaling",
+            "ms_per_step": ms, "pairs_per_s": A * A / (ms * 1e-3), "scaling": "strong",
+            "leading_block_max_err_vs_reference_fixture": err, "tolerance": 1e-10}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -208,11 +344,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     A, B, L, D, d = CFG["A"], CFG["B"], CFG["L"], CFG["D"], CFG["d"]
-    Xh, Yh = make_inputs(rank, torch)
-    Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
+    # every rank holds all rows of X (they are small); rank r solves rows [r*A, (r+1)*A)
+    Xs = [make_inputs(r, torch)[0] for r in range(world)]
+    Yh = make_inputs(0, torch)[1].pin_memory()
+    Xh = torch.cat(Xs, dim=0).pin_memory()
     Xd, Yd = Xh.to(dev), Yh.to(dev)
     sk = skb.SigKernel(skb.RBFKernel(CFG["sigma"]), d)
-    G_all = torch.empty((world * A, B), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     Gh = torch.empty((world * A, B), dtype=torch.float64).pin_memory()
 
@@ -221,20 +358,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        G = skb.ops.sigkernel_forward(Xd, Yd, "rbf", CFG["sigma"], d, "gram")
+    def gram(x, y):
         if world > 1:
-            dist.all_gather_into_tensor(G_all, G)
-            return G_all
-        return G
+            return skb.distributed.compute_Gram_sharded(sk, x, y)      # the package's sharded path (rows of X per rank)
+        return sk.compute_Gram(x, y)                                     # the public, reference-shaped API
+
+    def step_device():
+        return gram(Xd, Yd)
 
     def step_e2e():
         x = Xh.to(dev, non_blocking=True)
         y = Yh.to(dev, non_blocking=True)
-        G = sk.compute_Gram(x, y)                      # the public, reference-shaped API
-        if world > 1:
-            dist.all_gather_into_tensor(G_all, G)
-            G = G_all
+        G = gram(x, y)
         Gh.copy_(G, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return Gh
@@ -253,7 +388,6 @@ def run_ours(args):
     ev_k0.record(); ev_k1.record(); torch.cuda.synchronize()          # materialise the handles
     skb._lib.lib.skb_set_profile_events(ev_k0.cuda_event, ev_k1.cuda_event)
     barrier()                                           # all ranks enter the timed region together
-    t_wall0 = time.perf_counter()
     total_ms, kernel_ms = 0.0, 0.0
     for _ in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations
@@ -290,13 +424,21 @@ def run_ours(args):
     t_e2e = float(t.item())
     barrier()
 
+    # ---- the other BASELINE configs that have a GPU side ------------------------------------------
+    sub_steps = max(3, min(args.steps, 20))
+    cfg5 = bench_cfg5(skb, torch, dist, dev, world, rank, flush, sub_steps) if world > 1 else None
+    cfg4 = None
+    if world == 1:
+        peak_rate0 = max(peak["dadd"], peak["dmul"])
+        cfg4 = bench_cfg4(skb, torch, dev, flush, sub_steps, peak_rate0)
+
     if rank == 0:
         k_ms = kernel_ms / args.steps
-        w_full = dp_instr_per_pair(L, D, d) * A * B            # per launch (one rank's kernel)
-        w_sten = stencil_dp_instr_per_pair(L, d) * A * B
+        MM = (L - 1) << d
+        w_survey = 4.0 * A * B * MM * MM                        # 4 DP instructions per fine cell, nothing else
+        w_full = dp_instr_per_pair(L, D, d) * A * B             # what the formulation of skb_fwd5.cuh issues (3 per cell + static kernel)
         peak_rate = max(peak["dadd"], peak["dmul"])
-        achieved = w_full / (k_ms * 1e-3)
-        prof = os.path.join(ROOT, "profiles", "r01_fwd5_cfg3_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r02_fwd5_cfg3_summary.json")
         traffic = None
         if os.path.exists(prof):
             try:
@@ -304,46 +446,56 @@ def run_ours(args):
             except (ValueError, OSError):
                 traffic = None
         roofline = {
-            "bound": "fp64", "achieved": achieved / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
-            "frac": achieved / peak_rate, "traffic": traffic,
+            "bound": "fp64", "achieved": w_survey / (k_ms * 1e-3) / 1e12, "peak": peak_rate / 1e12, "unit": "T DP-instr/s",
+            "frac": w_survey / (k_ms * 1e-3) / peak_rate, "traffic": traffic,
+            "formula": "4 * A*B*MM*NN / kernel time / peak  (SURVEY.md 8(d): stencil only, 4 DP instructions per fine cell)",
             "kernel": "fwd5_kernel<RBF,RC=4,LOGD=2,DP2=3,NW=1,LPP=16>", "kernel_ms": k_ms,
             "peak_source": "measured live: register-resident DADD/DMUL chain (skb_fp64_probe); "
                            "MEASURED_PEAKS.json has no fp64 entry",
             "peak_dfma": peak["dfma"] / 1e12,
-            "achieved_stencil_only": w_sten / (k_ms * 1e-3) / 1e12,
-            "frac_stencil_only": w_sten / (k_ms * 1e-3) / peak_rate,
-            # SURVEY.md 8(d)'s conservative accounting: 4 DP instructions per fine cell, nothing else
-            "frac_survey_4_per_cell": (4.0 / 3.0) * w_sten / (k_ms * 1e-3) / peak_rate,
-            "dp_instr_per_pair": dp_instr_per_pair(L, D, d),
+            # the kernel's own accounting: 3 DP per cell (DADD, DMUL, DFMA) + coefficients + the static kernel
+            "frac_issued_dp": w_full / (k_ms * 1e-3) / peak_rate,
+            "frac_stencil_3_per_cell": 0.75 * w_survey / (k_ms * 1e-3) / peak_rate,
+            "dp_instr_per_pair_issued": dp_instr_per_pair(L, D, d),
             "hbm": {"algorithmic_bytes": 8 * (A * L * D + B * L * D + A * B),
                     "achieved_GBps": 8 * (A * L * D + B * L * D + A * B) / (k_ms * 1e-3) / 1e9,
                     "peak_GBps": _hbm_peak()},
         }
-        cores = host_cores()
-        rows = 16 if cores < 8 else 32
+        rows = 16
         try:
-            v_cpu, dt_cpu, kind, workers = cpu_gram_throughput(rows, 1)
-            cpu = {"value": v_cpu, "unit": UNIT, "cores": 1, "kind": kind,
-                   "sample": f"{rows} rows of X x 128 columns = {rows * B} pairs in {dt_cpu:.1f} s; "
-                             "static kernel + tile (torch) + single-threaded Cython/C solve, as the reference's CPU branch"}
-        except Exception as exc:  # the oracle is test infrastructure; its absence must not kill the bench
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+            if world > 1:
+                raise RuntimeError("the CPU baseline is timed at N = 1 only")
+            import torch as _t
+            threads = _t.get_num_threads()
+            v_cpu, dt_cpu, kind, workers = cpu_gram_throughput(rows, 1, threads)
+            _, how = cpu_path_description()
+            cpu = {"value": v_cpu, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": f"{rows} rows of X x 128 columns = {rows * B} pairs in {dt_cpu:.1f} s; {how}; one process, "
+                             f"{threads} torch threads for the static kernel and tile(), the PDE solve single-threaded as in the reference"}
+        except Exception as exc:  # the checker is test infrastructure; its absence must not kill the bench
+            cpu = None if world > 1 else {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": A * B, "pairs_per_step": pairs_per_step,
-                       "sharding": "rows of X per rank, Y replicated, one all_gather_into_tensor of G" if world > 1 else "single GPU",
+                       "api": ("sigkernel_b200.distributed.compute_Gram_sharded(SigKernel(RBFKernel(0.5), 2), X, Y): rows of X per "
+                               "rank, Y replicated, G reassembled on every rank") if world > 1 else
+                              "SigKernel(RBFKernel(0.5), 2).compute_Gram(X, Y) on device-resident tensors",
                        "l2": "flushed (256 MiB memset) between timed iterations; inputs are 0.5 MB"},
             "clocks": clocks,
             "e2e": {"value": pairs_per_step * args.steps / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": Xh.numel() * 8 + Yh.numel() * 8, "d2h_bytes_per_step": Gh.numel() * 8,
                     "ms_per_step": t_e2e / args.steps * 1e3,
-                    "api": "SigKernel(RBFKernel(0.5), 2).compute_Gram(X.cuda(), Y.cuda()) + .cpu()"},
-            "gpu_launches": 2 * args.steps,          # per step: prep2_kernel (paths + queue reset) and fwd5_kernel
+                    "api": "the same call on pinned host buffers: X.cuda(), Y.cuda(), compute_Gram, .cpu()"},
+            "gpu_launches": 2 * args.steps,          # per step and rank: prep2_kernel (paths + queue reset) and fwd5_kernel
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if cfg4 is not None:
+            line["cfg4"] = cfg4
+        if cfg5 is not None:
+            line["cfg5_sharded"] = cfg5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

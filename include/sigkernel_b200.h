@@ -74,9 +74,9 @@ void skb_set_warps_per_sm(int warps);
  * (the tile kernel is slower than fwd5_kernel at every BASELINE config so far). */
 void skb_set_tile_mode(int mode);
 
-/* Tuning / test knob (process-wide, default -1): which kernels serve the backward entry points.  -1 = adjoint by
- * reconstruction (16 lanes per pair where instantiated) with the stored-grid kernels queued as a device-side fallback,
- * 0 = stored-grid kernels only (round-1 behaviour), 1 = reconstruction with 32 lanes per pair only. */
+/* Tuning / test knob (process-wide, default -1): which kernels serve the backward entry points.  -1 (or 1) = adjoint by
+ * reconstruction (32 lanes per pair) with the stored-grid kernels queued as a device-side fallback, 0 = stored-grid
+ * kernels only (round-1 behaviour), 2 = reconstruction with 16 lanes per pair where instantiated. */
 void skb_set_adjoint_mode(int mode);
 
 /* Measurement hook (per calling thread): when both are non-NULL, every solver launch made by this thread records
@@ -144,6 +144,20 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype,
                       int A, int B, int M, int N, int D, int dyadic_order,
                       int static_kind, double static_param, int scheme, int pairs, int arith,
                       double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The same forward with the result written to SEVERAL destinations: out_peers is a HOST array of n_peers (<= 8) device
+ * pointers, each laid out like `out`; every k(X_a, Y_b) is stored to all of them.  This is the multi-GPU gather of
+ * sigkernel_b200.distributed without a collective: each rank passes, for every rank q, the address of ITS OWN row block
+ * inside q's copy of G (peer memory mapped through NVLink, e.g. torch symmetric memory), so the Gram matrix assembles
+ * itself on every rank while the solver runs; a barrier across the ranks afterwards is all that remains.
+ * GRAM / BATCH pairs, shapes served by fwd5_kernel (skb_forward_plan >= 4); SKB_ERR_UNSUPPORTED otherwise.
+ */
+int skb_sigkernel_fwd_peers(const void* X, const void* Y, int io_dtype,
+                            int A, int B, int M, int N, int D, int dyadic_order,
+                            int static_kind, double static_param, int scheme, int pairs,
+                            double* const* out_peers, int n_peers,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Plugin path: the caller evaluated an arbitrary static kernel itself

@@ -306,16 +306,18 @@ size_t skb_bwd_vjp_workspace_bytes(int A, int B, int M, int N, int D, int dyadic
     return bwd_workspace_bytes(A, B, M, N, D, dyadic_order, pairs, false, true);
 }
 
-int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
-                      int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
-                      int arith, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+static int sigkernel_fwd_impl(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
+                              int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
+                              int arith, double* out, double* const* out_peers, int n_peers, void* workspace,
+                              size_t workspace_bytes, void* stream) {
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, arith);
     if (rc) return rc;
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
     if (arith != SKB_ARITH_FMA) return SKB_ERR_BAD_ENUM;
-    if (!X || !Y || !out) return SKB_ERR_NULL;
+    if (!X || !Y || (!out && n_peers == 0)) return SKB_ERR_NULL;
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!out_peers || pairs == SKB_PAIRS_SYM))) return SKB_ERR_BAD_ENUM;
     const size_t fixed_bytes = kCounterBytes + align256((size_t)A * M * padded_dim(D) * sizeof(double)) +
                                align256((size_t)B * N * padded_dim(D) * sizeof(double));
     if (!workspace || workspace_bytes < fixed_bytes) return SKB_ERR_WORKSPACE;
@@ -328,7 +330,7 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     double cx, nsc;
     prep_factors(static_kind, static_param, cx, nsc);
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
-    const bool use_tile = tile_applies(kind, A, B, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1, pairs) &&
+    const bool use_tile = n_peers == 0 && tile_applies(kind, A, B, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1, pairs) &&
                           workspace_bytes >= fixed_bytes + tile_workspace_bytes(A, B, M, N, dyadic_order, pairs);
     const bool use5 = !use_tile && fwd5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
                       (size_t)A * M * padded_dim(D) * sizeof(double) < ((size_t)1 << 32) &&
@@ -345,6 +347,16 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
     a.Dp = Dp; a.D = D;
+    if (n_peers > 0) {
+        // results go straight to every rank's copy of G: only the fwd5 kernels have that output path
+        if (!use5) return SKB_ERR_UNSUPPORTED;
+        for (int q = 0; q < n_peers; ++q) {
+            if (!out_peers[q]) return SKB_ERR_NULL;
+            a.out_peer[q] = out_peers[q];
+        }
+        a.n_peer = n_peers;
+        return launch_forward5(kind, dyadic_order, a, st);
+    }
     if (use_tile) return launch_tile_forward(kind, dyadic_order, a, w + fixed_bytes, st);
     if (use5) return launch_forward5(kind, dyadic_order, a, st);
     if (solver_rows_per_lane(M, dyadic_order) >= 0) return launch_solver(MODE_FWD, kind, dyadic_order, false, a, st);
@@ -353,6 +365,21 @@ int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, 
     if (pairs == SKB_PAIRS_SYM) a.pairs = SKB_PAIRS_GRAM;
     return run_generic_forward(kind, a, dyadic_order, false, njobs_of(A, B, a.pairs), w + fixed_bytes,
                                workspace_bytes - fixed_bytes, st);
+}
+
+int skb_sigkernel_fwd(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
+                      int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
+                      int arith, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    return sigkernel_fwd_impl(X, Y, io_dtype, A, B, M, N, D, dyadic_order, static_kind, static_param, scheme, pairs, arith, out,
+                              nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+int skb_sigkernel_fwd_peers(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
+                            int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
+                            double* const* out_peers, int n_peers, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_peers <= 0) return SKB_ERR_BAD_ENUM;
+    return sigkernel_fwd_impl(X, Y, io_dtype, A, B, M, N, D, dyadic_order, static_kind, static_param, scheme, pairs, SKB_ARITH_FMA,
+                              nullptr, out_peers, n_peers, workspace, workspace_bytes, stream);
 }
 
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order, int scheme,

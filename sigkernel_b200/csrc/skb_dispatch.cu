@@ -301,10 +301,13 @@ static int pow2_ceil(int v) {
 
 // warps per pair (1, 2, 4; 0 = not covered), coarse rows per lane and lanes per pair of the reconstruction kernels:
 // SKB_RECON5_*_SHAPES of skb_recon5_launch.cuh (strips of at most 8 fine rows)
-static int recon5_plan(int M, int logd, int* rc_out, int* lpp_out) {
+static int recon5_plan(int mode, int M, int logd, int* rc_out, int* lpp_out) {
     if (logd > 3) return 0;
     const int rmax = 8 >> logd;
-    if (g_adjoint_mode != 1) {
+    // 16 lanes per pair (two pair streams per warp) wherever the strip is instantiated: the forward pass always, the
+    // reversed sweep only on request (mode 2; measured at 128 x 128 pairs of 64 points, dyadic order 1: 0.71 ms with 32
+    // lanes per pair, 0.89 ms with 16 -- twice the rows per lane do not pay for the larger, slower step there)
+    if (mode == MODE_FWD_EMIT || g_adjoint_mode == 2) {
         const int rc = pow2_ceil((M + 15) / 16);
         if (rc <= rmax && (rc << logd) >= 4) {
             *rc_out = rc; *lpp_out = 16;
@@ -335,12 +338,12 @@ bool recon5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     const int Dp = padded_dim(D);
     if (Dp != 4 && Dp != 6 && Dp != 10) return false;
     int rc, lpp;
-    return recon5_plan(M, logd, &rc, &lpp) > 0;
+    return recon5_plan(MODE_REV_RECON, M, logd, &rc, &lpp) > 0;
 }
 
 int launch_recon5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     int rc = 0, lpp = 32;
-    const int nw = recon5_plan(args.M, logd, &rc, &lpp);
+    const int nw = recon5_plan(mode, args.M, logd, &rc, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
     fill_v5_constants(args, logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;

@@ -151,6 +151,19 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //                   contract the per-point gradients with d loss / d K on the fly (gradX += coef * grad_points, atomic).
 // LPP = lanes per pair: 32 (default), or 16 -- then a warp carries TWO independent pair streams (lanes 0-15 and
 // 16-31), each lane owns twice the rows and the per-step overhead is spread over twice the cells.
+// the exchange buffer of a step: an std::integral_constant in the 3x unrolled loop (buffer offsets are immediates),
+// or a runtime int (UNR == 1: a third of the code, for the modes whose step is too large to unroll)
+template <class T> struct step_q {
+    static constexpr bool ct = true;
+    static constexpr int value = T::value;
+    static __device__ __forceinline__ int runtime(T) { return 0; }
+};
+template <> struct step_q<int> {
+    static constexpr bool ct = false;
+    static constexpr int value = 0;
+    static __device__ __forceinline__ int runtime(int q) { return q; }
+};
+
 template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0, int LPP = 32>
 __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     static_assert(LPP == 32 || (LPP == 16 && NW == 1 && (MODE == 0 || MODE == MODE_FWD_EMIT || MODE == MODE_REV_RECON)),
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // slot g+1 and reads the row above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0
     // needs no special case and a warp boundary (NW > 1) is just another slot; likewise the d value of the
     // first node row goes UP one lane.
-    static_assert(UNR == 3, "the exchange buffers and the d history rotate with period 3");
+    static_assert(UNR == 3 || UNR == 1, "the exchange buffers and the d history rotate with period 3 (UNR == 1: runtime buffer index)");
     constexpr int H = (F + 1) / 2;
     constexpr int NL = LPP == 32 ? 32 * NW : NSTR * (LPP + 1) - 1;   // exchange slots - 1
     constexpr int TXH = (NL + 1) * 16, TXQ = H * TXH;     // byte strides of tx[q][h][slot]
@@ -264,10 +277,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         row = row < M ? row : M - 1;
         xrow0[rc] = reinterpret_cast<const char*>(p.Xp) + (size_t)row * (Dp * 8);
     }
-    const unsigned txb = (unsigned)__cvta_generic_to_shared(&tx[0][0][slot]);   // read slot; write slot = +16
-    const unsigned dxb = (unsigned)__cvta_generic_to_shared(&dx[0][slot]);      // write slot; read slot = +8
-    const unsigned txrb = RECON ? (unsigned)__cvta_generic_to_shared(&txr[0][0][RECON ? slot : 0]) : 0u;
-    const unsigned sxrb = RECON ? (unsigned)__cvta_generic_to_shared(&sxr[0][RECON ? slot : 0]) : 0u;
+    const unsigned txb0 = (unsigned)__cvta_generic_to_shared(&tx[0][0][slot]);   // read slot; write slot = +16
+    const unsigned dxb0 = (unsigned)__cvta_generic_to_shared(&dx[0][slot]);      // write slot; read slot = +8
+    const unsigned txrb0 = RECON ? (unsigned)__cvta_generic_to_shared(&txr[0][0][RECON ? slot : 0]) : 0u;
+    const unsigned sxrb0 = RECON ? (unsigned)__cvta_generic_to_shared(&sxr[0][RECON ? slot : 0]) : 0u;
     constexpr int SXQ = (NL + 1) * 16;                      // byte stride of sxr[q][slot]
 
     double2 xr[XREG ? RC : 1][DP2];
@@ -330,6 +343,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // ---- REV_RECON: the rebuilt forward solution ub (reversed coordinates: ub(p', q') = u[MM - p', NN - q']) ----------
     double ub[RECON ? R : 1], topsb[RECON ? F : 1], topprevb = 1.0, bpre[RECON ? F : 1];
     double chk_tol = 0.0;                         // recon_tol * max(1, |k|) of the stencil stream's pair
+    double cur_coef = 0.0;                        // fused loss head: d loss / d k of the stencil stream's pair
+    double* cur_gx = nullptr;                     //                  and its rows of d loss / d X
 #pragma unroll
     for (int r = 0; r < (RECON ? R : 1); ++r) ub[r] = 1.0;
 #pragma unroll
@@ -483,7 +498,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // (NW > 1: split arrive/sync named barriers were measured slower than the plain block barrier: 6.1 vs
     // 4.65 ms at 64x512 pairs of len 128.)
     auto step = [&](auto qc) __attribute__((always_inline)) {
-        constexpr int Q = decltype(qc)::value;    // exchange buffer of this step
+        using QT = step_q<decltype(qc)>;
+        constexpr int Q = QT::value;              // exchange buffer of this step (0 + a runtime part when UNR == 1)
+        const int qr = QT::runtime(qc);
+        const unsigned txb = txb0 + (unsigned)(qr * TXQ), dxb = dxb0 + (unsigned)(qr * DXQ);
+        const unsigned txrb = txrb0 + (unsigned)(qr * TXQ), sxrb = sxrb0 + (unsigned)(qr * SXQ);
         // next step's stencil column is c+1: lane-1 needs this lane's first-row d[c+1] = dC as of NOW (made
         // one step ago), so this exchange does not wait for this step's production
         sts_f64<Q * DXQ>(dxb, REVX ? klast[0] - dC[0] : dC[0]);
@@ -676,7 +695,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             }
             // sensitivities of lane-1's last coarse row at the columns it finished in ITS previous step (= this lane's
             // columns c and c-1): written after the barrier of that step, read after this one
-            lds_f64x2<((Q + 2) % 3) * SXQ>(sxrb, up_c, up_c1);
+            if (QT::ct) lds_f64x2<((Q + 2) % 3) * SXQ>(sxrb0, up_c, up_c1);
+            else lds_f64x2<0>(sxrb0 + (unsigned)((qr == 0 ? 2 : qr - 1) * SXQ), up_c, up_c1);
         }
         {
             double vx, vy;
@@ -772,7 +792,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
                     if ((long)pl * R + r < MMl) bad = bad || !(fabs(ub[RECON ? r : 0] - 1.0) <= chk_tol);
-                if (bad) *p.flag = 1u;
+                // (a pair that contributes nothing -- zero weight in the loss head, no per-point gradients asked for -- may
+                //  miss: the diagonal of Gram(X, X) grows by orders of magnitude more than the rest and carries no weight
+                //  in the MMD and the scoring rules)
+                if (bad && (p.grad != nullptr || p.gradX == nullptr || cur_coef != 0.0)) *p.flag = 1u;
             }
             if (!REVX && cc == N - 2) {
                 // last coarse column done: u[MM, NN] is in the lane that owns grid row MM-1
@@ -786,6 +809,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         job_decode(p, p.job0 + sjob, a, b);
                         p.out[(long)a * p.B + b] = res;
                         p.out[(long)b * p.B + a] = res;
+                    } else if (p.n_peer > 0) {
+                        // one 8-byte store per rank: this pair's entry of every rank's copy of G (peer memory)
+                        for (int q = 0; q < p.n_peer; ++q) p.out_peer[q][p.job0 + sjob] = res;
                     } else {
                         p.out[p.job0 + sjob] = res;   // GRAM: job = a * B + b; BATCH: job = a
                     }
@@ -795,15 +821,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (REVX) {
                     // the pair is complete for this lane: emit its node rows (reversed order), clear the accumulators
                     const long pi = p.job0 + sjob;                      // GRAM: a * B + b; BATCH: a
-                    // REV_RECON: fused loss head -- d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
-                    double coef = 0.0;
-                    double* gx = nullptr;
-                    if (RECON && p.gradX != nullptr && sjob >= 0) {
-                        int a, b;
-                        job_decode(p, pi, a, b);
-                        coef = p.gout ? __ldg(p.gout + pi) : (a == b ? p.w_diag : p.w_off);
-                        gx = p.gradX + (long)a * M * D;
-                    }
+                    // REV_RECON: fused loss head -- d loss / d X_a += coef * d k(X_a, Y_b) / d X_a (coef and the rows of X_a
+                    // were looked up when the stencil stream moved on to this pair)
+                    const double coef = cur_coef;
+                    double* gx = (RECON && sjob >= 0) ? cur_gx : nullptr;
                     const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + sxo);
 #pragma unroll
                     for (int rc = 0; rc < RC; ++rc) {
@@ -821,7 +842,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                         const double gy = ga[GREG ? rc : 0][GREG ? k + 1 : 0];
                                         const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
                                         if (!RECON || gout) gout[k] = gv;
-                                        if (RECON && gxr) atomicAdd(gxr + k, coef * gv);
+                                        if (RECON && gxr && coef != 0.0) atomicAdd(gxr + k, coef * gv);
                                     }
                             } else {
                                 const double sW = acc[0];
@@ -829,7 +850,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                     const double gy = acc[(k + 1) * GL];
                                     const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
                                     if (!RECON || gout) gout[k] = gv;
-                                    if (RECON && gxr) atomicAdd(gxr + k, coef * gv);
+                                    if (RECON && gxr && coef != 0.0) atomicAdd(gxr + k, coef * gv);
                                 }
                             }
                         }
@@ -857,6 +878,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) ub[RECON ? r : 0] = bstg[(R - 1 - r) * GL + glane];
                     cbr = nbr;
+                    cur_coef = 0.0;
+                    cur_gx = nullptr;
+                    if (p.gradX != nullptr && pjob >= 0) {
+                        int a, b;
+                        job_decode(p, p.job0 + pjob, a, b);
+                        cur_coef = p.gout ? __ldg(p.gout + (p.job0 + pjob)) : (a == b ? p.w_diag : p.w_off);
+                        cur_gx = p.gradX + (long)a * M * D;
+                    }
                 }
                 c = 0;
                 sjob = pjob;
@@ -903,6 +932,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
     };
 
+    int qrun = 0;
 #pragma unroll 1
     while (true) {
         const bool alive = !done || sjob >= 0;
@@ -911,9 +941,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         } else {
             if (!__any_sync(FULL, alive)) break;
         }
-        step(std::integral_constant<int, 0>{});
-        step(std::integral_constant<int, 1>{});
-        step(std::integral_constant<int, 2>{});
+        if (UNR == 3) {
+            step(std::integral_constant<int, 0>{});
+            step(std::integral_constant<int, 1>{});
+            step(std::integral_constant<int, 2>{});
+        } else {
+            step(qrun);
+            qrun = qrun == 2 ? 0 : qrun + 1;
+        }
     }
 }
 

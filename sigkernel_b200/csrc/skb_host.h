@@ -53,6 +53,10 @@ struct KArgs {
     const double* gout;
     double* gradX;
     double w_diag, w_off;
+    // multi-GPU gather without a collective (forward, GRAM / BATCH): when n_peer > 0 every result is stored to each of
+    // out_peer[0 .. n_peer) (this rank's block inside every rank's copy of G, peer memory over NVLink) instead of `out`
+    double* out_peer[8];
+    int n_peer;
 };
 
 // records the cudaError_t for skb_last_cuda_error(); returns SKB_OK or SKB_ERR_CUDA
@@ -121,8 +125,8 @@ int launch_group_adj5_lin_store(int rc, int logd, int dp2, const KArgs&, cudaStr
 int launch_group_adj5_lin_rev(int rc, int logd, int dp2, const KArgs&, cudaStream_t);
 
 // ---- adjoint by reconstruction (MODE_FWD_EMIT / MODE_REV_RECON of skb_fwd5.cuh) ---------------------------------
-// development / tuning knob (process-wide): -1 = default (reconstruction, 16 lanes per pair when instantiated),
-// 0 = stored-grid kernels only, 1 = reconstruction with 32 lanes per pair only
+// development / tuning knob (process-wide): -1 / 1 = default (reconstruction, 32 lanes per pair), 0 = stored-grid
+// kernels only, 2 = reconstruction with 16 lanes per pair where instantiated
 void set_adjoint_mode(int mode);
 int get_adjoint_mode();
 // true if the reconstruction kernels cover the problem (fused kind, scheme S2, len_y >= 4, strips of <= 8 fine rows on

@@ -18,7 +18,8 @@ int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     // resident blocks per SM the register budget is sized for (the reversed sweep carries two solutions)
     constexpr int MINB = MODE == MODE_REV_RECON ? (NW > 1 ? (NW == 2 ? 4 : 2) : (R <= 4 ? 12 : 8))
                                                 : (NW > 1 ? (NW == 2 ? 8 : 4) : (R <= 4 ? 16 : 12));
-    constexpr int UNR = 3;
+    // the reversed sweep with 16 lanes per pair is too much code to unroll 3x (110 KB: it stalled on instruction fetch)
+    constexpr int UNR = (MODE == MODE_REV_RECON && LPP == 16) ? 1 : 3;
     int wpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() / NW : MINB;
     if (wpsm > MINB) wpsm = MINB;
     if (wpsm < 1) wpsm = 1;
@@ -30,7 +31,13 @@ int launch_recon5_one(const KArgs& a, cudaStream_t st) {
         constexpr bool GREG = RC * DP2 <= 6;
         smem = ((GREG ? 0 : (size_t)RC * (a.D + 1)) + (size_t)(R + 2)) * 32 * NW * sizeof(double);
     }
-    fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR, MODE, LPP><<<(unsigned)nb, 32 * NW, smem, st>>>(a);
+    auto kern = fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR, MODE, LPP>;
+    if (smem > 8 * 1024) {
+        // static + dynamic shared memory may pass the 48 KB a kernel gets without opting in (wide paths on 2 / 4 warps)
+        int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc) return rc;
+    }
+    kern<<<(unsigned)nb, 32 * NW, smem, st>>>(a);
     return check_launch();
 }
 

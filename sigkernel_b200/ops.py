@@ -56,6 +56,29 @@ def sigkernel_forward(X, Y, static_kind, static_param, dyadic_order, pairs="gram
     return out if pairs == "batch" else out.view(A, B)
 
 
+def sigkernel_forward_peers(X, Y, static_kind, static_param, dyadic_order, peer_ptrs, pairs="gram", naive=False):
+    """Forward whose results are stored to every address of `peer_ptrs` (device pointers laid out like the (A,B) /
+    (A,) output: this rank's block inside each rank's copy of G, see distributed.compute_Gram_sharded) instead of a local
+    tensor.  Returns False when the shape is outside the kernels that have this output path."""
+    import ctypes
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    if lib.skb_forward_plan(M, N, D, int(dyadic_order), _STATIC[static_kind], _lib.SCHEME_S1 if naive else _lib.SCHEME_S2) < 4:
+        return False
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs])
+    with torch.cuda.device(Xc.device):
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
+        rc = lib.skb_sigkernel_fwd_peers(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                         _STATIC[static_kind], float(static_param),
+                                         _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs],
+                                         ctypes.cast(arr, ctypes.c_void_p), len(peer_ptrs), ws.data_ptr(), nbytes, _stream())
+        if rc == -4:
+            return False
+        check(rc)
+    return True
+
+
 def sigkernel_forward_from_static(Ks, dyadic_order, pairs="gram", naive=False, exact=False):
     """Plugin path: Ks is the coarse static matrix (A,B,M,N) ('gram'/'sym') or (A,M,N) ('batch')."""
     if not Ks.is_cuda:

@@ -138,13 +138,14 @@ class _SigKernelGram(torch.autograd.Function):
         if spec is not None:
             kind, param, _ = spec
             if need_grad:
-                # forward over the triangle when symmetric (the grid of (b, a) is the transpose of that of (a, b));
-                # the reversed sweep later runs over every ordered pair
-                res = ops.sigkernel_forward_ctx(X, Y, kind, param, dyadic_order, pairs, _naive_solver)
+                # with gradients the full square is solved even when symmetric: the reversed sweep runs over every
+                # ordered pair and rebuilds each grid from ITS OWN last row / column (the transposed boundaries of (b, a)
+                # differ from those of (a, b) in the last bits, which the backward recurrence amplifies past the check)
+                res = ops.sigkernel_forward_ctx(X, Y, kind, param, dyadic_order, "gram", _naive_solver)
                 if res is not None:
                     G, bctx = res
                     ctx.mode = "lazy"
-                    ctx.meta = (kind, param, dyadic_order, _naive_solver, pairs)
+                    ctx.meta = (kind, param, dyadic_order, _naive_solver, "gram")
                     ctx.save_for_backward(X, Y, bctx)
                 else:
                     # like the reference, the whole backward is computed eagerly (sigkernel.py:397-399)
@@ -235,6 +236,8 @@ class _SigLoss(torch.autograd.Function):
         for first, second, pairs, w_diag, w_off, gscale in _SigLoss.terms(which, X.shape[0], Y.shape[0]):
             P, Q = T[first], T[second]
             if need_grad and gscale is not None:
+                if pairs == "sym":
+                    pairs = "gram"        # with gradients the full square is solved (see _SigKernelGram.forward)
                 G, bctx = ops.sigkernel_forward_ctx(P, Q, kind, param, dyadic_order, pairs, _naive_solver)
                 plan.append((second, pairs, w_diag, w_off, gscale, len(saved)))
                 saved.append(bctx)

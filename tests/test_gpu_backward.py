@@ -178,7 +178,9 @@ def test_cfg4_shape_properties(skb, O):
     _, gxx = skb.ops.sigkernel_forward_backward(Xd.detach(), Xd.detach(), "rbf", 0.5, 1, "gram")
     wxx = (torch.ones(n, n, dtype=torch.float64, device="cuda") - torch.eye(n, dtype=torch.float64, device="cuda")) / (n * (n - 1.))
     expect = 2 * torch.einsum('ab,abmd->amd', wxx, gxx) + torch.einsum('ab,abmd->amd', torch.full_like(wxx, -2. / (n * n)), gp)
-    assert grad_err(Xd.grad.cpu().numpy(), expect.cpu().numpy()) <= 1e-12
+    # (the fused loss head rebuilds the forward grids -- off-diagonal pairs to ~1e-10 of their size, the diagonal of K_XX
+    #  carries no weight -- where the eager call above falls back to the stored grid because of that diagonal)
+    assert grad_err(Xd.grad.cpu().numpy(), expect.cpu().numpy()) <= 1e-9
 
 
 # ---- adjoint by reconstruction (MODE_FWD_EMIT + MODE_REV_RECON), lazy fused backward, loss heads ------------------------
@@ -229,7 +231,7 @@ def test_reconstruction_agrees_with_the_stored_grid_kernels(skb):
         G0, gp0 = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, 1, "gram")
     finally:
         lib.skb_set_adjoint_mode(-1)
-    lib.skb_set_adjoint_mode(1)          # 32 lanes per pair
+    lib.skb_set_adjoint_mode(2)          # 16 lanes per pair
     try:
         G2, gp2 = skb.ops.sigkernel_forward_backward(X, Y, "rbf", 0.5, 1, "gram")
     finally:
@@ -277,10 +279,10 @@ def test_unstable_reconstruction_falls_back_to_the_stored_grid(skb, O):
     assert int(ws[64:68].view(torch.int32).item()) == 0
 
 
-def test_symmetric_gram_with_gradients_solves_the_triangle_once(skb, O):
-    """compute_Gram(X, X, sym=True) with X.requires_grad: forward over a <= b only; the reversed sweep of (a, b), a > b,
-    reads the transposed grid of (b, a).  Same values and gradient as the full square; the reference doubles the
-    gradient because Y (= X) requires grad (sigkernel.py:410-412)."""
+def test_symmetric_gram_with_gradients(skb, O):
+    """compute_Gram(X, X, sym=True) with X.requires_grad: same values and gradient as sym=False; the reference doubles
+    the gradient because Y (= X) requires grad (sigkernel.py:410-412).  The ABI can also run the reversed sweep from the
+    boundaries of a triangular forward (the pair (a, b), a > b, reads the transposed grid of (b, a))."""
     X = make_paths("rand", 95, (7, 21, 3))
     w = torch.rand(7, 7, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
     w = 0.5 * (w + w.T)
@@ -294,7 +296,14 @@ def test_symmetric_gram_with_gradients_solves_the_triangle_once(skb, O):
     assert fwd_err(Gs.detach().cpu().numpy(), Gf.detach().cpu().numpy()) <= 1e-12
     assert grad_err(Xs.grad.cpu().numpy(), Xf.grad.cpu().numpy()) <= 1e-11
     _, gp_ref, _ = O.gram_grad_points_analytic(X, X, O.RBFKernel(0.5), 1)
-    assert grad_err(Xs.grad.cpu().numpy(), O.gram_vjp(w, gp_ref, y_requires_grad=True).numpy()) <= GRAD_TOL_ANALYTIC
+    gref = O.gram_vjp(w, gp_ref, y_requires_grad=True)
+    assert grad_err(Xs.grad.cpu().numpy(), gref.numpy()) <= GRAD_TOL_ANALYTIC
+    # triangular forward + reversed sweep over the square, straight through ops
+    Xc = X.cuda()
+    Gt, bctx = skb.ops.sigkernel_forward_ctx(Xc, Xc, "rbf", 0.5, 1, "sym")
+    assert fwd_err(Gt.cpu().numpy(), Gf.detach().cpu().numpy()) <= 1e-12
+    gx = skb.ops.sigkernel_backward_vjp(Xc, Xc, "rbf", 0.5, 1, "gram", bctx, "sym", grad_out=w.cuda(), out_scale=2.0)
+    assert grad_err(gx.cpu().numpy(), gref.numpy()) <= 1e-8
     # sym=True with two different tensors is NOT symmetric: it must not take the triangular shortcut
     Y = make_paths("rand", 96, (7, 21, 3)).cuda()
     G_bad = sk.compute_Gram(X.cuda(), Y, sym=True)

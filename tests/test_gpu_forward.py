@@ -328,7 +328,8 @@ def test_fwd5_shapes_vs_oracle(skb, O, A, B, M, N, D, d, static):
     if A == B:
         assert fwd_err(sk.compute_kernel(X.cuda(), Y.cuda()).cpu().numpy(), O.compute_kernel(X, Y, ok, d).numpy()) <= FWD_TOL
         if M == N:
-            Gs = sk.compute_Gram(X.cuda(), X.cuda(), sym=True)
+            Xc = X.cuda()
+            Gs = sk.compute_Gram(Xc, Xc, sym=True)
             assert torch.equal(Gs, Gs.T)
             assert fwd_err(Gs.cpu().numpy(), O.compute_Gram(X, X, ok, d).numpy()) <= FWD_TOL
 

@@ -29,9 +29,27 @@ def _worker(rank, world, port, q):
         X = torch.rand((13, 20, 3), dtype=torch.float64, generator=g).cuda()
         Y = torch.rand((9, 17, 3), dtype=torch.float64, generator=g).cuda()
         sk = skb.SigKernel(skb.RBFKernel(0.5), 1)
+        ok = []
+        # ragged split (13 rows over 2 ranks): padded NCCL all-gather
         G = skb.distributed.compute_Gram_sharded(sk, X, Y)
-        ref = sk.compute_Gram(X, Y)
-        q.put((rank, bool(torch.equal(G, ref))))
+        ok.append(bool(torch.equal(G, sk.compute_Gram(X, Y))) and skb.distributed.last_gather == "all_gather")
+        # even split: the solver stores straight into every rank's symmetric-memory copy of G, no collective; several calls
+        # in a row alternate between the two copies
+        for k in range(5):
+            Xk = X[:12] * (1.0 + 0.01 * k)
+            G = skb.distributed.compute_Gram_sharded(sk, Xk, Y)
+            ref = sk.compute_Gram(Xk, Y)
+            ok.append(bool(torch.equal(G, ref)))
+        path = skb.distributed.last_gather
+        # with gradients the NCCL path (and its autograd-aware gather) is taken
+        Xg = X[:12].clone().requires_grad_(True)
+        Gg = skb.distributed.compute_Gram_sharded(sk, Xg, Y)
+        Gg.sum().backward()
+        lo, hi = skb.distributed.row_block(12, rank, world)
+        Xr = X[:12].clone().requires_grad_(True)
+        sk.compute_Gram(Xr, Y).sum().backward()
+        ok.append(bool(torch.allclose(Xg.grad[lo:hi], Xr.grad[lo:hi], rtol=1e-10, atol=1e-12)) and bool((Xg.grad[:lo] == 0).all()))
+        q.put((rank, all(ok), path))
     finally:
         dist.destroy_process_group()
 
@@ -47,4 +65,6 @@ def test_sharded_gram_two_gpus_nccl():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert dict(q.get(timeout=5) for _ in range(2)) == {0: True, 1: True}
+    res = [q.get(timeout=5) for _ in range(2)]
+    assert {r[0]: r[1] for r in res} == {0: True, 1: True}, res
+    print("gather path on NCCL:", res[0][2])

@@ -12,6 +12,8 @@ CFG = {"cfg4": (128, 128, 64, 3, 1), "cfg3b": (128, 128, 64, 5, 2), "cfg2b": (64
 
 
 def main():
+    if os.environ.get('SKB_ADJ_MODE'):
+        skb._lib.lib.skb_set_adjoint_mode(int(os.environ['SKB_ADJ_MODE']))
     for name in (sys.argv[1:] or list(CFG)):
         A, B, L, D, d = CFG[name]
         g = torch.Generator().manual_seed(0)
