@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     for (int f = 0; f < (RECON ? F : 1); ++f) { topsb[f] = 1.0; bpre[f] = 1.0; }
     // boundary arrays of the stencil stream's pair (cbr: row reached through lane 0's top; set at the re-arm) and of the
     // pair the production stream is in (nbr / nbc: fixed when the production column wraps, 4 steps before the re-arm)
-    const double* cbr = p.brow;
+    const double* cbr = p.brow + F;               // lane 0: next step's part of the last row (walks down, F values per step)
+    bool cbr_ok = false;
     const double* nbr = p.brow;
     const double* nbc = p.bcol;
     // staging of a lane's first column u[., NN] (R + 1 values incl. the node above the strip, then u[MM, NN] = k itself,
@@ -508,14 +509,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         sts_f64<Q * DXQ>(dxb, REVX ? klast[0] - dC[0] : dC[0]);
         if (RECON) {
             // lane 0 of the pair: the rebuilt row above its strip is the forward solution's LAST ROW -- the values of
-            // the NEXT step are loaded now (a step of latency hiding) and replace what the exchange delivers
-            const bool wrapn = c == N - 1;
-            const int jn_ = wrapn ? pjob : sjob;
-            const int cn = wrapn ? 0 : c + 1;
-            const double* brn = wrapn ? nbr : cbr;
-            const bool okb = pl == 0 && jn_ >= 0 && cn < N - 1;
+            // the NEXT step are loaded now (a step of latency hiding) and replace what the exchange delivers.  cbr walks
+            // down the row, F values per step; on the step without a coarse column it jumps to the next pair's row.
+            if (c == N - 1) {
+                cbr = nbr + (NNf - 1);
+                cbr_ok = pjob >= 0;
+            }
+            const bool okb = pl == 0 && cbr_ok && c != N - 2;
 #pragma unroll
-            for (int f = 0; f < (RECON ? F : 1); ++f) bpre[f] = okb ? __ldg(brn + (NNf - (long)cn * F - f - 1)) : 1.0;
+            for (int f = 0; f < (RECON ? F : 1); ++f) bpre[f] = okb ? __ldg(cbr - f) : 1.0;
+            cbr -= F;
         }
         const bool real_col = sjob >= 0 && c < N - 1;
         if (REVG && !STAGE) load_fw(sjob, c);
@@ -722,6 +725,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 const bool ok = !dummy && (pl * RC + rc < M - 1);
                 Scur[rc] = ok ? t * p.scale4 : 0.0;
             }
+            double2 ysv[GREG ? DP2 : 1];
+            if (GREG) {
+#pragma unroll
+                for (int i = 0; i < DP2; ++i) ysv[GREG ? i : 0] = ldg2(syp + 2 * i);
+            }
 #pragma unroll
             for (int rc = 0; rc < RC; ++rc) {
                 const double uc = rc > 0 ? Scur[rc > 0 ? rc - 1 : 0] : up_c;
@@ -732,7 +740,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     // the prepared y row is (norm term, y_1 .. y_D, 0 ...): slot 0 accumulates W itself
 #pragma unroll
                     for (int i = 0; i < DP2; ++i) {
-                        const double2 yv = ldg2(syp + 2 * i);
+                        const double2 yv = ysv[GREG ? i : 0];
                         ga[GREG ? rc : 0][GREG ? 2 * i : 0] = fma(W, i == 0 ? 1.0 : yv.x, ga[GREG ? rc : 0][GREG ? 2 * i : 0]);
                         ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = fma(W, yv.y, ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0]);
                     }
@@ -877,7 +885,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     chk_tol = p.recon_tol * fmax(1.0, fabs(bstg[(R + 1) * GL + glane]));
 #pragma unroll
                     for (int r = 0; r < R; ++r) ub[RECON ? r : 0] = bstg[(R - 1 - r) * GL + glane];
-                    cbr = nbr;
                     cur_coef = 0.0;
                     cur_gx = nullptr;
                     if (p.gradX != nullptr && pjob >= 0) {
