@@ -232,17 +232,19 @@ def measure_fp64_peak(skb, torch):
 
 
 def _time_steps(torch, fn, steps, flush, barrier):
-    """CUDA-event time of `steps` calls of fn, L2 flushed before each; returns total ms (this rank)."""
-    total = 0.0
+    """Device time of `steps` calls of fn in ms (this rank): every call sits between its own pair of CUDA events with an L2
+    flush (256 MiB memset) before it; the whole sequence is enqueued first and synchronised once, so the host (Python,
+    launch latency, jitter between ranks) is not in the loop."""
+    evs = []
     for _ in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        total += e0.elapsed_time(e1)
-    return total
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs)
 
 
 def bench_cfg4(skb, torch, dev, flush, steps, peak_rate):
@@ -384,20 +386,24 @@ def run_ours(args):
     t_load0 = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         step_device()
-    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev_k0.record(); ev_k1.record(); torch.cuda.synchronize()          # materialise the handles
-    skb._lib.lib.skb_set_profile_events(ev_k0.cuda_event, ev_k1.cuda_event)
     barrier()                                           # all ranks enter the timed region together
-    total_ms, kernel_ms = 0.0, 0.0
+    # EXACTLY `steps` steps, each between its own CUDA events (and the solver kernel between a second pair, recorded by the
+    # library around its launch), L2 flushed before each; enqueued as one sequence and synchronised once at the end
+    evs, kevs = [], []
     for _ in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(); k1.record()                        # materialise the handles
+        skb._lib.lib.skb_set_profile_events(k0.cuda_event, k1.cuda_event)
         e0.record()
         step_device()
         e1.record()
-        torch.cuda.synchronize()
-        total_ms += e0.elapsed_time(e1)
-        kernel_ms += ev_k0.elapsed_time(ev_k1)
+        evs.append((e0, e1))
+        kevs.append((k0, k1))
+    torch.cuda.synchronize()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kevs)
     t_wall1 = time.perf_counter()
     skb._lib.lib.skb_set_profile_events(None, None)
     barrier()
@@ -482,7 +488,8 @@ def run_ours(args):
                        "api": ("sigkernel_b200.distributed.compute_Gram_sharded(SigKernel(RBFKernel(0.5), 2), X, Y): rows of X per "
                                "rank, Y replicated, G reassembled on every rank") if world > 1 else
                               "SigKernel(RBFKernel(0.5), 2).compute_Gram(X, Y) on device-resident tensors",
-                       "l2": "flushed (256 MiB memset) between timed iterations; inputs are 0.5 MB"},
+                       "l2": "flushed (256 MiB memset) between timed iterations; inputs are 0.5 MB",
+                       "timing": "CUDA events around every step, steps enqueued back to back, one synchronise at the end, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": pairs_per_step * args.steps / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": Xh.numel() * 8 + Yh.numel() * 8, "d2h_bytes_per_step": Gh.numel() * 8,

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr bool SCALED = (MODE == 0 || EMIT) && NW == 1 && XREGq && Rq > 8;
     constexpr int ETAB = SCALED ? EXP_TAB5 : EXP_TAB;
     __shared__ double etab[ETAB];                // RBF: kscale * 2^(j/ETAB)
-    __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset, -) in bytes
+    __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset in bytes, row a of the pair)
     // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
     // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
     // slot g+1 and reads the row above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0
@@ -241,11 +241,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     const unsigned xstride = (unsigned)(M * Dp * 8), ystride = (unsigned)(N * Dp * 8);   // bytes (< 4 GB: host check)
     int job_next = 0;
     unsigned xo, yo;                              // byte offsets of the production pair's paths
+    int pa = 0;                                   // REV_RECON: row a of the production pair (b follows from the job index)
     {
         int a, b;
         job_decode(p, p.job0 + (has_job ? first_job : 0), a, b);
         xo = (unsigned)a * xstride;
         yo = (unsigned)b * ystride;
+        pa = a;
         if (pl == 0) {
             for (int q = 0; q < 3; ++q) {
                 for (int h = 0; h < H; ++h) tx[q][h][slot] = make_double2(1.0, 1.0);
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     sxr[RECON ? q : 0][RECON ? slot : 0] = make_double2(0.0, 0.0);
                 }
             }
-            ring_s[sid][0] = make_int4(has_job ? first_job : -1, (int)xo, (int)yo, 0);
+            ring_s[sid][0] = make_int4(has_job ? first_job : -1, (int)xo, (int)yo, pa);
             job_next = has_job ? (int)(G + atomicAdd(p.counter, 1u)) : p.njobs;
         }
     }
@@ -365,8 +367,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             long sl = p.job0 + (job_ >= 0 ? job_ : 0);
             bool swp = false;
             if (p.bsym) {
-                int a, b;
-                job_decode(p, sl, a, b);
+                const int a = pa, b = (int)(sl - (long)pa * p.B);      // bsym: GRAM enumeration (no division: a rides in the ring)
                 swp = a > b;
                 const long lo = swp ? b : a, hi = swp ? a : b;
                 sl = lo * p.A - lo * (lo - 1) / 2 + (hi - lo);
@@ -834,14 +835,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     const double coef = cur_coef;
                     double* gx = (RECON && sjob >= 0) ? cur_gx : nullptr;
                     const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + sxo);
+                    double* gpair = p.grad ? p.grad + pi * (long)(M * D) : nullptr;     // one 64-bit product per pair, int offsets per row
 #pragma unroll
                     for (int rc = 0; rc < RC; ++rc) {
                         const int np = pl * RC + rc;                    // reversed node row
                         double* acc = gacc + (rc * (D + 1)) * GL + glane;
                         if (sjob >= 0 && np < M) {
-                            double* gout = p.grad ? p.grad + (pi * M + (M - 1 - np)) * D : nullptr;
-                            double* gxr = gx ? gx + (long)(M - 1 - np) * D : nullptr;
-                            const double* xrw = sxb + (long)np * Dp;
+                            const int go = (M - 1 - np) * D;
+                            double* gout = gpair ? gpair + go : nullptr;
+                            double* gxr = gx ? gx + go : nullptr;
+                            const double* xrw = sxb + np * Dp;
                             if (GREG) {
                                 const double sW = ga[GREG ? rc : 0][0];
 #pragma unroll
@@ -888,8 +891,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     cur_coef = 0.0;
                     cur_gx = nullptr;
                     if (p.gradX != nullptr && pjob >= 0) {
-                        int a, b;
-                        job_decode(p, p.job0 + pjob, a, b);
+                        const int a = pa;
+                        const int b = p.pairs == PAIRS_BATCH ? a : (int)(p.job0 + pjob - (long)a * p.B);
                         cur_coef = p.gout ? __ldg(p.gout + (p.job0 + pjob)) : (a == b ? p.w_diag : p.w_off);
                         cur_gx = p.gradX + (long)a * M * D;
                     }
@@ -900,7 +903,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             if (cc == pc) {
                 // the production column wraps: next pair
                 ++w;
-                int4 ent = make_int4(-1, (int)xo, (int)yo, 0);
+                int4 ent = make_int4(-1, (int)xo, (int)yo, pa);
                 if (pl == 0) {
                     int job = job_next;
                     if (job < p.njobs) {
@@ -909,6 +912,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         job_decode(p, p.job0 + job, a, b);
                         ent.y = (int)((unsigned)a * xstride);
                         ent.z = (int)((unsigned)b * ystride);
+                        ent.w = a;
                     } else {
                         job = -1;
                     }
@@ -921,6 +925,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (w >= 0 && ent.x < 0) done = true;
                 xo = (unsigned)ent.y;
                 yo = (unsigned)ent.z;
+                if (RECON) pa = ent.w;
                 set_pair();                       // virtual / past the end: the same pair's data again
                 if (RECON) {
                     pair_boundaries(pjob);
