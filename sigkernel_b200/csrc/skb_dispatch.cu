@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "skb_common.cuh"
 #include "skb_host.h"
 #include "skb_tile.cuh"
@@ -252,7 +253,28 @@ bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
     return fwd5_plan(M, logd, nullptr) > 0;
 }
 
-static void fill_v5_constants(KArgs& args, int logd) {
+// 2^(j/2048), j = 0..2047, in device memory: every block of the RBF kernels copies (a stride of) it, times kscale, into
+// its shared exp table instead of evaluating exp2 64 times per lane.  Built once per device on first use (host libm,
+// synchronous copy); the pointer stays valid for the life of the process.
+static const double* device_exp_table() {
+    static std::mutex mu;
+    static const double* tabs[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (tabs[dev]) return tabs[dev];
+    static double host[2048];
+    for (int j = 0; j < 2048; ++j) host[j] = exp2((double)j / 2048.0);
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(host)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    tabs[dev] = d;
+    return d;
+}
+
+static int fill_v5_constants(KArgs& args, int logd) {
+    args.exp_tab = device_exp_table();
+    if (!args.exp_tab) return SKB_ERR_CUDA;
     args.kscale = fwd5_kscale(logd);
     args.inv_kscale = 1.0 / args.kscale;
     args.sqrt3 = sqrt(3.0);
@@ -261,6 +283,7 @@ static void fill_v5_constants(KArgs& args, int logd) {
     args.elo = -0x1.a39ef35793c76p-41;
     args.e4 = 1.0 / 24.0;
     args.e3 = 1.0 / 6.0;
+    return SKB_OK;
 }
 
 // SKB_ADJ5_SHAPES of skb_fwd5.cuh: one warp per pair, dyadic order >= 1, <= 8 fine rows per lane
@@ -277,7 +300,7 @@ bool adjoint5_applies(int kind, int M, int N, int D, int logd, bool s1) {
 
 int launch_adjoint5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     const int rcp = coarse_rows_per_lane(args.M);
-    fill_v5_constants(args, logd);
+    if (int e = fill_v5_constants(args, logd)) return e;
     args.pitch = 32L * (rcp << logd);
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int rc = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
@@ -345,7 +368,7 @@ int launch_recon5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     int rc = 0, lpp = 32;
     const int nw = recon5_plan(mode, args.M, logd, &rc, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
-    fill_v5_constants(args, logd);
+    if (int e = fill_v5_constants(args, logd)) return e;
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int err = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (err) return err;
@@ -400,7 +423,7 @@ int launch_forward5(int kind, int logd, KArgs args, cudaStream_t st) {
     int rcp = 0, lpp = 32;
     const int nw = fwd5_plan(args.M, logd, &rcp, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
-    fill_v5_constants(args, logd);
+    if (int e = fill_v5_constants(args, logd)) return e;
     if (fwd5_scaled_exp(args.M, logd, args.D)) {
         // single-warp forward variants with the x rows in registers: exp argument in units of c = ln2 / 2048 (exp_scaled5): e^(r c) - 1 = r (c + r (c^2/2 + r c^3/6))
         const double c = 0.693147180559945309417232121458 / 2048.0;

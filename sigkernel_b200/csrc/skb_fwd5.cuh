@@ -48,10 +48,23 @@ namespace skb {
 // Keep in sync with adjoint5_shape_ok() (skb_dispatch.cu).
 #define SKB_ADJ5_SHAPES(X) X(1, 1) X(1, 2) X(1, 3) X(2, 1) X(2, 2)
 
+// Table lookup of the two exp variants below.  Entry j of the table holds kscale * 2^(j/TAB) with (j << SH) taken off
+// its high word (SH = 20 - log2 TAB), so that adding (ti << SH), ti = TAB n + j, restores the entry AND scales it by
+// 2^n in one integer instruction; the entry's shared address is a mask and one multiply-add.
+template <int TAB>
+__device__ __forceinline__ double exp_tab_entry(int ti, unsigned tab_s) {
+    constexpr int SH = TAB == 2048 ? 9 : (TAB == 256 ? 12 : -1);
+    static_assert(SH > 0, "table sizes: 256, 2048");
+    int lo, hi;
+    asm("{\n\t.reg .b32 j, a;\n\tand.b32 j, %2, %3;\n\tmad.lo.u32 a, j, 8, %4;\n\tld.shared.v2.b32 {%0, %1}, [a];\n\t}"
+        : "=r"(lo), "=r"(hi) : "r"(ti), "n"(TAB - 1), "r"(tab_s));
+    return __hiloint2double(hi + (ti << SH), lo);
+}
+
 // exp(x) for x <= ~0, table-driven as exp_neg(); the underflow guard clamps x to >= -700.x through an
 // unsigned min on the high word (negative doubles order like their unsigned high words); NaN (canonical,
 // sign clear) passes through.
-__device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ tab, const KArgs& p) {
+__device__ __forceinline__ double exp_neg5(double x, unsigned tab_s, const KArgs& p) {
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
     const unsigned hi = min((unsigned)__double2hiint(x), 0xC085E000u);
     const double xc = __hiloint2double((int)hi, __double2loint(x));
@@ -63,17 +76,15 @@ __device__ __forceinline__ double exp_neg5(double x, const double* __restrict__ 
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = q * r;
-    const int ti = __double2loint(t);                    // 256 n + j
-    const double tj = tab[ti & (EXP_TAB - 1)];
-    const double v = fma(tj, q, tj);
-    return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB - 1)) * 4096, __double2loint(v));
+    const double tj = exp_tab_entry<EXP_TAB>(__double2loint(t), tab_s);   // lo(t) = 256 n + j: kscale 2^n 2^(j/256)
+    return fma(tj, q, tj);
 }
 
 // Forward mode (MODE 0): the exp argument arrives pre-scaled by 2048 / ln 2 (folded into the prepared rows), so the
 // range reduction is three additions (no hi/lo split of ln 2) and a 2^11-entry table leaves a degree-3 polynomial:
 // 7 DP instructions instead of 9.  The guard clamps xs to >= -2031616 (x >= -687.6); NaN passes through.
 constexpr int EXP_TAB5 = 2048;
-__device__ __forceinline__ double exp_scaled5(double xs, const double* __restrict__ tab, const KArgs& p) {
+__device__ __forceinline__ double exp_scaled5(double xs, unsigned tab_s, const KArgs& p) {
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
     const unsigned hi = min((unsigned)__double2hiint(xs), 0xC13F0000u);
     const double xc = __hiloint2double((int)hi, __double2loint(xs));
@@ -83,10 +94,8 @@ __device__ __forceinline__ double exp_scaled5(double xs, const double* __restric
     double q = fma(r, p.e3, p.e4);                       // e4 = c^2/2, e3 = c^3/6, ek = c = ln2 / 2048 (forward mode)
     q = fma(q, r, p.ek);
     q = q * r;                                           // e^(r c) - 1, truncation 3.4e-17
-    const int ti = __double2loint(t);
-    const double tj = tab[ti & (EXP_TAB5 - 1)];
-    const double v = fma(tj, q, tj);
-    return __hiloint2double(__double2hiint(v) + (ti & ~(EXP_TAB5 - 1)) * 512, __double2loint(v));
+    const double tj = exp_tab_entry<EXP_TAB5>(__double2loint(t), tab_s);
+    return fma(tj, q, tj);
 }
 
 // shared-memory accesses of the neighbour exchange: 32-bit shared addresses with compile-time offsets, so that
@@ -210,7 +219,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // blocks per SM: room for 16 KB each) whose x rows live in registers.  Keep in sync with fwd5_scaled_exp().
     constexpr bool SCALED = (MODE == 0 || EMIT) && NW == 1 && XREGq && Rq > 8;
     constexpr int ETAB = SCALED ? EXP_TAB5 : EXP_TAB;
-    __shared__ double etab[ETAB];                // RBF: kscale * 2^(j/ETAB)
+    __shared__ double etab[ETAB];   // RBF: kscale * 2^(j/ETAB), high word less j << SH (exp_tab_entry)
+    const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
     __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset in bytes, row a of the pair)
     // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
     // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
@@ -229,7 +239,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     __shared__ double2 txr[RECON ? 3 : 1][RECON ? H : 1][RECON ? NL + 1 : 1];
     __shared__ double2 sxr[RECON ? 3 : 1][RECON ? NL + 1 : 1];
     if (KIND == KIND_RBF) {
-        for (int j = glane; j < ETAB; j += 32 * NW) etab[j] = p.kscale * exp2((double)j * (1.0 / ETAB));
+        for (int j = glane; j < ETAB; j += 32 * NW) {
+            const double e = p.kscale * __ldg(p.exp_tab + j * (2048 / ETAB));
+            etab[j] = __hiloint2double(__double2hiint(e) - (j << (ETAB == 2048 ? 9 : 12)), __double2loint(e));
+        }
     }
 
     // ---- job stream -------------------------------------------------------------------------------
@@ -770,7 +783,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 xv = XREG ? xr[XREG ? rc : 0][i] : (XSM ? xs_s[XSM ? rc * DP2 + i : 0][XSM ? glane : 0] : ldg2(xrow[(XREG || XSM) ? 0 : rc] + 2 * i));
                 acc = fma(xv.y, yq[i].y, fma(xv.x, yq[i].x, acc));
             }
-            if (KIND == KIND_RBF) acc = SCALED ? exp_scaled5(acc, etab, p) : exp_neg5(acc, etab, p);
+            if (KIND == KIND_RBF) acc = SCALED ? exp_scaled5(acc, etab_s, p) : exp_neg5(acc, etab_s, p);
             dnew[rc] = REVX ? klast[rc] : acc - klast[rc];      // reversed sweeps: the history rotates k itself
             klast[rc] = acc;
         }

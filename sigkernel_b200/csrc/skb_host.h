@@ -37,6 +37,7 @@ struct KArgs {
     // the coefficient polynomial and of the table-driven exp live here so that they are constant-bank operands
     double kscale, sqrt3, inv_kscale;
     double ek, ehi, elo, e4, e3;
+    const double* exp_tab;   // 2^(j/2048), j < 2048 (device_exp_table(), skb_dispatch.cu)
     // adjoint by reconstruction (MODE_FWD_EMIT / MODE_REV_RECON of skb_fwd5.cuh): the forward pass leaves the last row
     // and the last column of every pair's grid, brow[slot][k] = u[MM, k] (k = 0..NN) and bcol[slot][k] = u[k, NN]
     // (k = 0..MM); the reversed sweep rebuilds the grid backwards from them.  slot = job index of the forward launch.

@@ -95,6 +95,31 @@ __global__ void __launch_bounds__(256) fp64_probe_mix_kernel(int iters, double s
 }
 }  // namespace skb
 
+namespace skb {
+// dependent-issue latency: C independent chains of 16 / C DFMAs each per iteration (OP 10: C = 1, 11: C = 2, 12: C = 4,
+// 13: C = 8); thread-level DP instructions per launch as for the other variants (16 per iteration).  Run with one
+// warp per scheduler: time per instruction = max(issue interval, latency / C).
+template <int C>
+__global__ void __launch_bounds__(256) fp64_probe_chain_kernel(int iters, double seed, double* sink) {
+    double v[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) v[i] = seed + (double)(threadIdx.x + i) * 1e-9;
+    const double a = 1.0 + seed * 1e-12, b = seed * 1e-13;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 16 / C; ++rep) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) v[i] = fma(v[i], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < C; ++i) s += v[i];
+    if (s == 123.456) sink[0] = s;
+}
+}  // namespace skb
+
 extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream) {
     using namespace skb;
     if (blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0) return SKB_ERR_BAD_SHAPE;
@@ -110,6 +135,10 @@ extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double
     else if (op == 7) fp64_probe_mix_kernel<7><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 8) fp64_probe_mix_kernel<8><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 9) fp64_probe_mix_kernel<9><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 10) fp64_probe_chain_kernel<1><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 11) fp64_probe_chain_kernel<2><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 12) fp64_probe_chain_kernel<4><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 13) fp64_probe_chain_kernel<8><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else return SKB_ERR_BAD_ENUM;
     return check_launch();
 }
