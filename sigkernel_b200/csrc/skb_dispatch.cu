@@ -369,6 +369,13 @@ int launch_recon5(int mode, int kind, int logd, KArgs args, cudaStream_t st) {
     const int nw = recon5_plan(mode, args.M, logd, &rc, &lpp);
     if (nw == 0) return SKB_ERR_UNSUPPORTED;
     if (int e = fill_v5_constants(args, logd)) return e;
+    {
+        // parked-sum buffers of the reversed sweep: the first lane of a warp is up to 31 steps (+ the step of the boundary
+        // check) ahead of the flush, i.e. ceil(34 / N) pairs
+        int nbuf = 1;
+        while (nbuf * args.N < 34) nbuf *= 2;
+        args.fbuf_mask = nbuf - 1;
+    }
     if (!args.counter) return SKB_ERR_WORKSPACE;
     int err = args.counter_clean ? SKB_OK : check_cuda(cudaMemsetAsync(args.counter, 0, sizeof(unsigned int), st));
     if (err) return err;

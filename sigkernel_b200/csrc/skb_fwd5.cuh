@@ -193,6 +193,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int DEPTH = (F * R <= 8) ? 4 : (F * R <= 16 ? 2 : 1);
     constexpr int NP = F * R / 2;                // 16-byte pieces per lane and step
     constexpr bool GREG = REVX && (RC * DP2 <= 6);   // gradient accumulators in registers instead of shared memory
+    // REV_RECON with register accumulators: a lane that finishes a pair only parks its sums (and the rebuilt first column,
+    // for the boundary check) in shared memory; the warp emits the gradient rows of the pair together, once its last
+    // lane is through -- the epilogue runs once per pair and warp instead of once per pair and LANE (the lanes are
+    // skewed, so every per-lane event costs the warp a full pass with one lane active)
+    constexpr bool UFLUSH = RECON && GREG;
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= ((LPP == 16 && R > 8) ? 12 : 8));   // x rows of the pair in registers (the 16-row
                                                                            // strips run 8 warps per SM: room for 12 double2)
@@ -373,6 +378,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // staging of a lane's first column u[., NN] (R + 1 values incl. the node above the strip, then u[MM, NN] = k itself,
     // the scale of the boundary check): [k][lane] behind gacc
     double* const bstg = RECON ? gacc + (GREG ? 0 : (size_t)RC * (D + 1) * GL) : nullptr;
+    // UFLUSH: parked sums [buffer][rc * DP2 + i][lane] (double2) and first columns [buffer][r][lane], buffer = pair index
+    // mod (fbuf_mask + 1) -- as many buffers as pairs fit between a lane's event and the flush of its warp (host: N (mask + 1) >= 34)
+    constexpr int FBUF = (RC * Dp + R) * GL;      // doubles per buffer
+    double* const gst = UFLUSH ? bstg + (size_t)(R + 2) * GL : nullptr;
     auto pair_boundaries = [&](int job_) {
         // slot of the pair in the forward launch's boundary arrays; under bsym the pair (a, b), a > b, reads the
         // transposed grid of (b, a)
@@ -807,7 +816,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     if ((long)pl * R + r < MMl) bc[r] = u[r];
                 if (pl == 0) bc[-1] = 1.0;
             }
-            if (RECON && cc == N - 2 && sjob >= 0) {
+            if (UFLUSH && cc == N - 2) {
+                // the rebuilt first column u[., 0] of the pair (checked against the boundary value 1 in the flush)
+                double* us = gst + (size_t)((w - 1) & p.fbuf_mask) * FBUF + RC * Dp * GL + glane;
+#pragma unroll
+                for (int r = 0; r < R; ++r) us[r * GL] = ub[RECON ? r : 0];
+            }
+            if (RECON && !UFLUSH && cc == N - 2 && sjob >= 0) {
                 // the rebuilt grid must end at the boundary u[., 0] = 1: a miss beyond recon_tol * max(1, |k|) (errors scale with
                 // the size of the solution; or a NaN) sends the whole call to the stored-grid kernels queued behind this one
                 bool bad = false;
@@ -840,7 +855,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 }
             }
             if (cc == N - 1) {
-                if (REVX) {
+                if (UFLUSH) {
+                    double2* gs = reinterpret_cast<double2*>(gst + (size_t)((w - 1) & p.fbuf_mask) * FBUF) + glane;
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc)
+#pragma unroll
+                        for (int i = 0; i < DP2; ++i) {
+                            gs[(rc * DP2 + i) * GL] = make_double2(ga[GREG ? rc : 0][GREG ? 2 * i : 0], ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0]);
+                            ga[GREG ? rc : 0][GREG ? 2 * i : 0] = 0.0;
+                            ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = 0.0;
+                        }
+                    syo = yo;
+                    syp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + syo);
+                }
+                if (REVX && !UFLUSH) {
                     // the pair is complete for this lane: emit its node rows (reversed order), clear the accumulators
                     const long pi = p.job0 + sjob;                      // GRAM: a * B + b; BATCH: a
                     // REV_RECON: fused loss head -- d loss / d X_a += coef * d k(X_a, Y_b) / d X_a (coef and the rows of X_a
@@ -898,12 +926,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     // the production column wrapped), and that pair's last row for lane 0
                     cp_async_wait<0>();
                     topprevb = bstg[R * GL + glane];
-                    chk_tol = p.recon_tol * fmax(1.0, fabs(bstg[(R + 1) * GL + glane]));
+                    if (!UFLUSH) chk_tol = p.recon_tol * fmax(1.0, fabs(bstg[(R + 1) * GL + glane]));
 #pragma unroll
                     for (int r = 0; r < R; ++r) ub[RECON ? r : 0] = bstg[(R - 1 - r) * GL + glane];
                     cur_coef = 0.0;
                     cur_gx = nullptr;
-                    if (p.gradX != nullptr && pjob >= 0) {
+                    if (!UFLUSH && p.gradX != nullptr && pjob >= 0) {
                         const int a = pa;
                         const int b = p.pairs == PAIRS_BATCH ? a : (int)(p.job0 + pjob - (long)a * p.B);
                         cur_coef = p.gout ? __ldg(p.gout + (p.job0 + pjob)) : (a == b ? p.w_diag : p.w_off);
@@ -943,6 +971,71 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (RECON) {
                     pair_boundaries(pjob);
                     stage_first_column(pjob >= 0);
+                }
+            }
+        }
+        if (UFLUSH) {
+            // ---- 5b. flush: the last lane of the warp has just parked pair fw -- the warp emits its gradient rows ----
+            const int fwl = __shfl_sync(FULL, cc == N - 1 ? w : 0, LPP - 1, LPP);   // (w >= 1 once a real pair is complete)
+            if (fwl > 0) {
+                const int fw = fwl - 1;
+                const int4 ent = ring_s[sid][fw & (RING - 1)];
+                if (ent.x >= 0) {
+                    const long pi = p.job0 + ent.x;                      // GRAM: a * B + b; BATCH: a
+                    const int a = ent.w;
+                    const int b = p.pairs == PAIRS_BATCH ? a : (int)(pi - (long)a * p.B);
+                    // fused loss head: d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
+                    const double coef = p.gradX == nullptr ? 0.0 : (p.gout ? __ldg(p.gout + pi) : (a == b ? p.w_diag : p.w_off));
+                    double* gx = p.gradX ? p.gradX + (long)a * (M * D) : nullptr;
+                    double* gpair = p.grad ? p.grad + pi * (long)(M * D) : nullptr;
+                    const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + (unsigned)ent.y);
+                    const double* fs = gst + (size_t)(fw & p.fbuf_mask) * FBUF + glane;
+                    const double2* fs2 = reinterpret_cast<const double2*>(gst + (size_t)(fw & p.fbuf_mask) * FBUF) + glane;
+                    // the rebuilt grid must end at the boundary u[., 0] = 1: a miss beyond recon_tol * max(1, |k|) (errors scale
+                    // with the size of the solution; or a NaN) sends the whole call to the stored-grid kernels queued behind
+                    // this one.  (A pair that contributes nothing -- zero weight in the loss head, no per-point gradients
+                    // asked for -- may miss: the diagonal of Gram(X, X) grows by orders of magnitude more than the rest and
+                    // carries no weight in the MMD and the scoring rules.)
+                    if (p.grad != nullptr || p.gradX == nullptr || coef != 0.0) {
+                        long sl = pi;
+                        bool swp = false;
+                        if (p.bsym) {
+                            swp = a > b;
+                            const long lo = swp ? b : a, hi = swp ? a : b;
+                            sl = lo * p.A - lo * (lo - 1) / 2 + (hi - lo);
+                        }
+                        const double kab = swp ? __ldg(p.brow + sl * p.brow_stride + NNf) : __ldg(p.bcol + sl * p.bcol_stride + MMl);
+                        const double tol = p.recon_tol * fmax(1.0, fabs(kab));
+                        bool bad = false;
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if ((long)pl * R + r < MMl) bad = bad || !(fabs(fs[(RC * Dp + r) * GL] - 1.0) <= tol);
+                        if (bad) *p.flag = 1u;
+                    }
+#pragma unroll
+                    for (int rc = 0; rc < RC; ++rc) {
+                        const int np = pl * RC + rc;                    // reversed node row
+                        if (np < M && (gpair != nullptr || coef != 0.0)) {
+                            const int go = (M - 1 - np) * D;
+                            const double* xrw = sxb + np * Dp;
+                            double gsum[Dp];                            // [0]: sum of W; [1 + k]: sum of W y_k
+#pragma unroll
+                            for (int i = 0; i < DP2; ++i) {
+                                const double2 v = fs2[(rc * DP2 + i) * GL];
+                                gsum[2 * i] = v.x;
+                                gsum[2 * i + 1] = v.y;
+                            }
+                            const double sW = gsum[0];
+#pragma unroll
+                            for (int k = 0; k < Dp - 1; ++k)
+                                if (k < D) {
+                                    const double gy = gsum[k + 1];
+                                    const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(p.gscale, gy, -(__ldg(xrw + 1 + k) * sW)) : p.gscale * gy;
+                                    if (gpair) gpair[go + k] = gv;
+                                    if (coef != 0.0) atomicAdd(gx + go + k, coef * gv);
+                                }
+                        }
+                    }
                 }
             }
         }

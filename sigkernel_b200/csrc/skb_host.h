@@ -48,6 +48,7 @@ struct KArgs {
                                      // index of (min, max); a > b reads the transposed grid: brow <-> bcol)
     unsigned int* flag;              // REV_RECON: set to 1 if a rebuilt grid misses u[., 0] = 1 by more than recon_tol
     double recon_tol;
+    int fbuf_mask;                   // REV_RECON: parked-sum buffers - 1 (a power of two with N * buffers >= 34; skb_fwd5.cuh UFLUSH)
     const unsigned int* cond;        // if non-NULL the kernel returns at once unless *cond != 0 (stored-grid fallback)
     // fused loss head of REV_RECON: gradX[a, m, :] += coef(a,b) * grad_points[a, b, m, :] (atomic), with
     // coef = gout[pair] if gout, else (a == b ? w_diag : w_off)

@@ -30,6 +30,7 @@ int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     if (MODE == MODE_REV_RECON) {
         constexpr bool GREG = RC * DP2 <= 6;
         smem = ((GREG ? 0 : (size_t)RC * (a.D + 1)) + (size_t)(R + 2)) * 32 * NW * sizeof(double);
+        if (GREG) smem += (size_t)(a.fbuf_mask + 1) * (RC * 2 * DP2 + R) * 32 * NW * sizeof(double);   // parked sums + first columns
     }
     auto kern = fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR, MODE, LPP>;
     if (smem > 8 * 1024) {
