@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     __shared__ double etab[ETAB];   // RBF: kscale * 2^(j/ETAB), high word less j << SH (exp_tab_entry)
     const unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
     __shared__ int4 ring_s[NSTR][RING];          // job stream: (job, x offset, y offset in bytes, row a of the pair)
+    __shared__ longlong2 ring_b[RECON ? NSTR : 1][RECON ? RING : 1];   // REV_RECON: (last row, last column) of the pair's forward grid
     // Neighbour exchange through shared memory, triple-buffered (buffer = position in the 3x unrolled loop;
     // one warp / block barrier per step separates the writes from the reads): lane g writes its bottom row to
     // slot g+1 and reads the row above its strip from slot g -- slot 0 holds the boundary u = 1, so lane 0
@@ -386,9 +387,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         // slot of the pair in the forward launch's boundary arrays; under bsym the pair (a, b), a > b, reads the
         // transposed grid of (b, a)
         if (RECON) {
-            long sl = p.job0 + (job_ >= 0 ? job_ : 0);
+            long sl = job_ >= 0 ? p.job0 + job_ : 0;      // (virtual / past the end: slot 0, nothing is read from it)
             bool swp = false;
-            if (p.bsym) {
+            if (p.bsym && job_ >= 0) {
                 const int a = pa, b = (int)(sl - (long)pa * p.B);      // bsym: GRAM enumeration (no division: a rides in the ring)
                 swp = a > b;
                 const long lo = swp ? b : a, hi = swp ? a : b;
@@ -403,13 +404,18 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     auto stage_first_column = [&](bool real) {
         if (RECON) {
             // ub[r] = u[MM - pl R - r - 1, NN] (r = -1 .. R-1) = nbc[MM - pl R - R + k], k = 0 .. R
+            // entries of rows above the grid (strips past its end) are zero-filled: no bytes are read for them, and the
+            // clamped base keeps even their addresses inside the boundary arrays
             const long i0 = MMl - (long)(pl + 1) * R;
+            const double* nb = nbc + (i0 < -(R + 1) ? -(R + 1) : (int)i0);
+            const int kmin = i0 < -(R + 1) ? R + 1 : (i0 < 0 ? (int)-i0 : 0);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(bstg + glane);
 #pragma unroll
-            for (int k = 0; k <= R + 1; ++k) {
-                const bool ok = real && (k > R || i0 + k >= 0);
-                const double* src = ok ? nbc + (k > R ? MMl : i0 + k) : p.bcol;
+            for (int k = 0; k <= (UFLUSH ? R : R + 1); ++k) {
+                const bool ok = real && (k > R || k >= kmin);
+                const double* src = k > R ? nbc + MMl : nb + k;
                 const int n8 = ok ? 8 : 0;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bstg + k * GL + glane)), "l"(src), "r"(n8) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (unsigned)(k * GL * 8)), "l"(src), "r"(n8) : "memory");
             }
             cp_async_commit();
         }
@@ -417,6 +423,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     if (RECON) {
         // lane 0 of a pair starts inside its first pair (no production wrap before the first re-arm)
         pair_boundaries(pjob);
+        if (pl == 0) ring_b[RECON ? sid : 0][0] = make_longlong2((long long)nbr, (long long)nbc);   // read >= 1 step (1 barrier) later
         stage_first_column(pjob >= 0);
     }
     // Layout of the stored grid (v5 adjoint): LANE-major, [job][forward lane t][fine column q][R rows] -- each
@@ -534,10 +541,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             // lane 0 of the pair: the rebuilt row above its strip is the forward solution's LAST ROW -- the values of
             // the NEXT step are loaded now (a step of latency hiding) and replace what the exchange delivers.  cbr walks
             // down the row, F values per step; on the step without a coarse column it jumps to the next pair's row.
-            if (c == N - 1) {
-                cbr = nbr + (NNf - 1);
-                cbr_ok = pjob >= 0;
-            }
+            // (cbr jumps to the next pair's row in the event block of the step before the column without a coarse column)
             const bool okb = pl == 0 && cbr_ok && c != N - 2;
 #pragma unroll
             for (int f = 0; f < (RECON ? F : 1); ++f) bpre[f] = okb ? __ldg(cbr - f) : 1.0;
@@ -816,6 +820,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     if ((long)pl * R + r < MMl) bc[r] = u[r];
                 if (pl == 0) bc[-1] = 1.0;
             }
+            if (RECON && cc == N - 2 && pl == 0) {
+                cbr = nbr + (NNf - 1);
+                cbr_ok = pjob >= 0;
+            }
             if (UFLUSH && cc == N - 2) {
                 // the rebuilt first column u[., 0] of the pair (checked against the boundary value 1 in the flush)
                 double* us = gst + (size_t)((w - 1) & p.fbuf_mask) * FBUF + RC * Dp * GL + glane;
@@ -959,8 +967,19 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     }
                     ent.x = job;
                     ring_s[sid][w & (RING - 1)] = ent;
+                    if (RECON) {
+                        // lane 0 looks the pair's boundary arrays up for everybody
+                        pa = ent.w;
+                        pair_boundaries(job);
+                        ring_b[RECON ? sid : 0][RECON ? (w & (RING - 1)) : 0] = make_longlong2((long long)nbr, (long long)nbc);
+                    }
                 } else if (w >= 0) {
                     ent = ring_s[sid][w & (RING - 1)];     // written >= 1 step (= 1 barrier) ago
+                    if (RECON) {
+                        const longlong2 eb = ring_b[RECON ? sid : 0][RECON ? (w & (RING - 1)) : 0];
+                        nbr = reinterpret_cast<const double*>(eb.x);
+                        nbc = reinterpret_cast<const double*>(eb.y);
+                    }
                 }
                 pjob = ent.x;
                 if (w >= 0 && ent.x < 0) done = true;
@@ -968,10 +987,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 yo = (unsigned)ent.z;
                 if (RECON) pa = ent.w;
                 set_pair();                       // virtual / past the end: the same pair's data again
-                if (RECON) {
-                    pair_boundaries(pjob);
-                    stage_first_column(pjob >= 0);
-                }
+                if (RECON) stage_first_column(pjob >= 0);
             }
         }
         if (UFLUSH) {
