@@ -95,11 +95,13 @@ int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, voi
  *                                               1 = register-resident solver_kernel (v4),
  *                                               4 = fwd5_kernel with 16 lanes per pair (two pairs per warp),
  *                                               5 / 6 / 7 = fwd5_kernel with 1 / 2 / 4 warps per pair;
- *   skb_adjoint_plan  (skb_sigkernel_fwd_bwd): -4 (SKB_ERR_UNSUPPORTED) = shape not covered by the backward,
- *                                               1 = solver_kernel store / reversed modes (v4),
+ *   skb_adjoint_plan  (skb_sigkernel_fwd_bwd): 1 = solver_kernel store / reversed modes (v4),
  *                                               5 = fwd5_kernel store / reversed modes,
  *                                               6 = adjoint by reconstruction (fwd5_kernel MODE_FWD_EMIT + MODE_REV_RECON;
- *                                                   no stored grid, (len_x - 1) 2^d <= 1024 at dyadic order <= 2).
+ *                                                   no stored grid, (len_x - 1) 2^d <= 1024 at dyadic order <= 2),
+ *                                               7 = every other length: the reference's algebra on materialised grids
+ *                                                   (forward grid, reversed grid, pooled product; skb_generic_adj.cu) --
+ *                                                   no shape is refused, skb_sigkernel_fwd_bwd only.
  * Negative values are SKB_ERR_* codes for bad arguments. */
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
 int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);

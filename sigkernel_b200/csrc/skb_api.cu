@@ -240,7 +240,7 @@ int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int
     if (scheme != SKB_SCHEME_S2 && scheme != SKB_SCHEME_S1) return SKB_ERR_BAD_ENUM;
     const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
     if (recon5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1)) return 6;
-    if (solver_rows_per_lane(M, dyadic_order) < 0) return SKB_ERR_UNSUPPORTED;
+    if (solver_rows_per_lane(M, dyadic_order) < 0) return 7;      // materialised grids (skb_generic_adj.cu): any length
     return adjoint5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) ? 5 : 1;
 }
 
@@ -276,14 +276,63 @@ size_t skb_ctx_bytes(int A, int B, int M, int N, int dyadic_order, int pairs) {
     return align256((size_t)njobs_of(A, B, pairs) * (ctx_row_doubles(N, dyadic_order) + ctx_col_doubles(M, dyadic_order)) * sizeof(double));
 }
 
+// ---- backward on materialised grids (any shape; skb_generic_adj.cu) -----------------------------------------------
+static const size_t kMaterializedBudget = (size_t)2 << 30;
+static size_t materialized_doubles_per_pair(int M, int N, int d) {
+    const size_t MMf = (size_t)(M - 1) << d, NNf = (size_t)(N - 1) << d;
+    return (size_t)M * N + 2 * (size_t)(M - 1) * (N - 1) + 2 * (MMf + 1) * (NNf + 1);
+}
+
+// a.Xp / a.Yp prepared (forward orientation, plain prep_factors), a.gscale set; out (njobs), grad (njobs, M, D)
+static int run_materialized_adjoint(int kind, const KArgs& a, int d, long njobs, double* out, double* grad, char* scratch,
+                                    size_t scratch_bytes, cudaStream_t st) {
+    const int M = a.M, N = a.N;
+    if ((((long)(M - 1)) << d) > 0x3fffffffL || (((long)(N - 1)) << d) > 0x3fffffffL) return SKB_ERR_BAD_SHAPE;
+    const size_t per = materialized_doubles_per_pair(M, N, d) * sizeof(double);
+    if (scratch_bytes < per + 512) return SKB_ERR_WORKSPACE;
+    long chunk = (long)((scratch_bytes - 512) / per);
+    if (chunk > njobs) chunk = njobs;
+    if (chunk > 0x3fffffffL) chunk = 0x3fffffffL;
+    double* base = (double*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    const size_t grid = (size_t)((((long)(M - 1)) << d) + 1) * (size_t)((((long)(N - 1)) << d) + 1);
+    for (long j0 = 0; j0 < njobs; j0 += chunk) {
+        const long nj = njobs - j0 < chunk ? njobs - j0 : chunk;
+        double* Ks = base;
+        double* incc = Ks + (size_t)nj * M * N;
+        double* S = incc + (size_t)nj * (M - 1) * (N - 1);
+        double* U = S + (size_t)nj * (M - 1) * (N - 1);
+        (void)grid;
+        int rc = launch_static_matrix(a, kind, j0, nj, Ks, st);
+        if (rc) return rc;
+        rc = launch_coarse_increments(Ks, incc, nj, M, N, a.scale4, false, st);
+        if (rc) return rc;
+        rc = launch_grid_solve(incc, U, out, j0, nj, M, N, d, a.s1 != 0, st);
+        if (rc) return rc;
+        rc = launch_coarse_sens(U, S, nj, M, N, d, a.scale4, st);
+        if (rc) return rc;
+        rc = launch_grad_from_sens(S, Ks, a, kind, grad, j0, nj, st);
+        if (rc) return rc;
+    }
+    return SKB_OK;
+}
+
 // fixed part: counter block, prepared paths in both orientations, [boundary context]; then the stored-grid scratch
 static size_t bwd_workspace_bytes(int A, int B, int M, int N, int D, int d, int pairs, bool with_ctx, bool with_vjp) {
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || d < 0) return 0;
     const long nj = njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
     const bool recon = recon_ok(SKB_STATIC_RBF, A, B, M, N, D, d, SKB_SCHEME_S2);
     const size_t grid_b = grid_doubles_per_pair(M, N, d) * sizeof(double);
-    if (!recon && grid_b == 0) return 0;
     const size_t Dp = (size_t)padded_dim(D);
+    if (!recon && grid_b == 0) {
+        // materialised-grid backward (skb_sigkernel_fwd_bwd only): prepared paths + a chunk of pairs
+        if (with_vjp) return 0;
+        const size_t per = materialized_doubles_per_pair(M, N, d) * sizeof(double);
+        size_t jobs = (size_t)nj;
+        size_t cap = kMaterializedBudget / per;
+        if (cap < 1) cap = 1;
+        if (jobs > cap) jobs = cap;
+        return kCounterBytes + align256((size_t)A * M * Dp * sizeof(double)) + align256((size_t)B * N * Dp * sizeof(double)) + jobs * per + 1024;
+    }
     size_t w = kCounterBytes + 2 * align256((size_t)A * M * Dp * sizeof(double)) + 2 * align256((size_t)B * N * Dp * sizeof(double));
     if (recon && with_ctx) w += skb_ctx_bytes(A, B, M, N, d, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
     if (with_vjp) w += align256((size_t)nj * sizeof(double)) + align256((size_t)A * M * D * sizeof(double));   // k of the fallback's forward pass; this call's gradient
@@ -482,7 +531,24 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     const bool recon = recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme);
     const bool stored = solver_rows_per_lane(M, dyadic_order) >= 0;
-    if (!recon && !stored) return SKB_ERR_UNSUPPORTED;
+    if (!recon && !stored) {
+        // outside every register-resident adjoint kernel: the reference's algebra on materialised grids
+        const int Dpm = padded_dim(D);
+        const size_t xbm = align256((size_t)A * M * Dpm * sizeof(double)), ybm = align256((size_t)B * N * Dpm * sizeof(double));
+        if (workspace_bytes < kCounterBytes + xbm + ybm) return SKB_ERR_WORKSPACE;
+        char* wm = (char*)workspace;
+        double* Xm = (double*)(wm + kCounterBytes);
+        double* Ym = (double*)(wm + kCounterBytes + xbm);
+        double cxm, nscm;
+        prep_factors(static_kind, static_param, cxm, nscm);
+        rc = launch_prep2(X, Y, io_dtype, Xm, nullptr, Ym, nullptr, A, M, B, N, D, Dpm, cxm, nscm, (unsigned int*)wm, st);
+        if (rc) return rc;
+        KArgs ma = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+        ma.Xp = Xm; ma.Yp = Ym; ma.Dp = Dpm; ma.D = D;
+        ma.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
+        return run_materialized_adjoint(static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, ma, dyadic_order, nj, out, grad_points,
+                                        wm + kCounterBytes + xbm + ybm, workspace_bytes - (kCounterBytes + xbm + ybm), st);
+    }
     const size_t ctxb = recon ? skb_ctx_bytes(A, B, M, N, dyadic_order, pairs) : 0;
     const size_t fixed = kCounterBytes + 2 * xb + 2 * yb + ctxb;
     if (workspace_bytes < fixed) return SKB_ERR_WORKSPACE;

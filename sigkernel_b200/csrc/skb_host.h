@@ -83,6 +83,10 @@ int solver_rows_per_lane(int M, int logd);
 // generic fallback: coarse increments (pairs, M-1, N-1) from a static matrix; static matrix of the fused kinds
 int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, int N, double scale4, bool exact, cudaStream_t st);
 int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double* Ks, cudaStream_t st);
+// backward on materialised grids (skb_generic_adj.cu)
+int launch_grid_solve(const double* inc, double* U, double* out, long job0, long njobs, int M, int N, int d, bool s1, cudaStream_t st);
+int launch_coarse_sens(const double* U, double* S, long njobs, int M, int N, int d, double scale4, cudaStream_t st);
+int launch_grad_from_sens(const double* S, const double* Ks, const KArgs& a, int kind, double* grad, long job0, long njobs, cudaStream_t st);
 // padded row width the fused kinds are specialised for
 int padded_dim(int D);
 

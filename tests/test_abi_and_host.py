@@ -79,7 +79,11 @@ def test_workspace_sizes():
     finally:
         lib.skb_set_adjoint_mode(-1)
     assert lib.skb_bwd_vjp_workspace_bytes(128, 128, 64, 64, 3, 1, 0) > 0
-    assert lib.skb_bwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) == 0        # unsupported shape says so
+    # beyond the register-resident kernels: materialised grids, any length (plan 7); only the eager entry point takes them
+    per = (2000 * 8 + 2 * 1999 * 7 + 2 * 2000 * 8) * 8
+    assert 4 * per <= lib.skb_bwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) <= 4 * per + (1 << 20)
+    assert lib.skb_adjoint_plan(2000, 8, 2, 0, 1, 0) == 7 and lib.skb_adjoint_plan(300, 9, 2, 2, 0, 0) == 7
+    assert lib.skb_bwd_vjp_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) == 0
     assert lib.skb_aux_workspace_bytes(2, 2, 8, 8, 1, 0) >= 4
     # shapes outside the register-resident kernels get the generic row-band workspace
     assert lib.skb_fwd_workspace_bytes(2, 2, 2000, 8, 2, 0, 0) > lib.skb_fwd_workspace_bytes(2, 2, 200, 8, 2, 0, 0)
@@ -197,8 +201,8 @@ def test_dispatch_plans_for_the_baseline_configs():
     assert lib.skb_adjoint_plan(1000, 6, 2, 0, RBF, S2) == 6     # the reference's own limit: (len_x - 1) 2^d < 1024
     assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S1) == 1      # _naive_solver: stored-grid v4 kernels
     assert lib.skb_adjoint_plan(64, 3, 3, 1, RBF, S2) == 1       # len_y < 4
-    assert lib.skb_adjoint_plan(2000, 6, 2, 0, RBF, S2) == -4    # backward not covered (SKB_ERR_UNSUPPORTED)
-    assert lib.skb_adjoint_plan(300, 6, 2, 2, RBF, S2) == -4     # 1196 fine rows
+    assert lib.skb_adjoint_plan(2000, 6, 2, 0, RBF, S2) == 7     # any other length: materialised grids (never unsupported)
+    assert lib.skb_adjoint_plan(300, 6, 2, 2, RBF, S2) == 7      # 1196 fine rows
     lib.skb_set_adjoint_mode(0)
     try:
         assert lib.skb_adjoint_plan(64, 64, 3, 1, RBF, S2) == 5      # stored grid on the v5 kernels

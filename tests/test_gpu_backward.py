@@ -222,6 +222,34 @@ def test_reconstruction_adjoint_vs_analytic_oracle(skb, O, A, B, M, N, D, d, sta
     assert grad_err(gx.cpu().numpy(), expect.cpu().numpy()) <= 1e-12
 
 
+ANY_LENGTH = [
+    # A, B, M, N, D, d, naive    beyond every register-resident adjoint kernel: materialised grids (skb_generic_adj.cu)
+    (2, 2, 300, 12, 2, 2, False), (1, 2, 600, 9, 3, 1, False), (1, 1, 1000, 7, 2, 1, False), (2, 1, 1100, 5, 4, 0, False),
+    (1, 2, 70, 11, 3, 4, False), (2, 2, 300, 6, 2, 2, True),
+]
+
+
+@pytest.mark.parametrize("A,B,M,N,D,d,naive", ANY_LENGTH)
+@pytest.mark.parametrize("static", ["rbf", "linear"])
+def test_backward_of_any_length_vs_analytic_oracle(skb, O, A, B, M, N, D, d, naive, static):
+    X = make_paths("bm", 700 + M, (A, M, D))
+    Y = make_paths("bm", 800 + N, (B, N, D))
+    ok = O.RBFKernel(0.9) if static == "rbf" else O.LinearKernel()
+    par = 0.9 if static == "rbf" else 1.0
+    assert skb.ops.adjoint_plan(M, N, D, d, static, naive) == 7
+    Gref, gp_ref, _ = O.gram_grad_points_analytic(X, Y, ok, d, naive=naive)
+    G, gp = skb.ops.sigkernel_forward_backward(X.cuda(), Y.cuda(), static, par, d, "gram", naive)
+    assert fwd_err(G.cpu().numpy(), Gref.numpy()) <= FWD_TOL
+    assert grad_err(gp.cpu().numpy(), gp_ref.numpy()) <= GRAD_TOL_ANALYTIC
+    # and through autograd: d (sum w G) / d X
+    Xg = X.cuda().requires_grad_(True)
+    sk = skb.SigKernel(skb.RBFKernel(0.9) if static == "rbf" else skb.LinearKernel(), d, _naive_solver=naive)
+    w = torch.linspace(-1.0, 2.0, A * B, dtype=torch.float64).reshape(A, B)
+    (sk.compute_Gram(Xg, Y.cuda()) * w.cuda()).sum().backward()
+    expect = torch.einsum('ab,abmd->amd', w, gp_ref)
+    assert grad_err(Xg.grad.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
+
+
 def test_reconstruction_agrees_with_the_stored_grid_kernels(skb):
     X, Y = make_paths("rand", 81, (6, 40, 3)).cuda(), make_paths("rand", 82, (5, 33, 3)).cuda()
     lib = skb._lib.lib
