@@ -162,6 +162,26 @@ int skb_sigkernel_fwd_peers(const void* X, const void* Y, int io_dtype,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * One slice [job_lo, job_hi) of the pair enumeration of `pairs` -- a rank's share of a sharded Gram matrix.  GRAM: job =
+ * a * B + b; BATCH: job = a; SYM: the pairs a <= b, row by row (job = a * A - a (a - 1) / 2 + (b - a)) -- equal slices of
+ * the SYM enumeration are equal amounts of work, which contiguous row blocks of a symmetric matrix are not.
+ * Results go to `out` (n_peers == 0; laid out like the full matrix, entries of other jobs are left alone) or to every
+ * pointer of out_peers (n_peers > 0, as skb_sigkernel_fwd_peers; each points to the START of a rank's full copy); SYM
+ * writes both mirror entries.  Shapes served by fwd5_kernel (skb_forward_plan >= 4); SKB_ERR_UNSUPPORTED otherwise.
+ * sig_peers (may be NULL; needs n_peers > 0): HOST array of n_peers device pointers, rank q's array of n_peers 64-bit
+ * signal slots (peer memory, zero before the first call).  The solver kernel then ENDS with the barrier across the ranks:
+ * its last block stores sig_epoch (> 0, increasing from call to call) to slot my_rank of every rank's array and waits until
+ * all slots of its own array have reached sig_epoch -- when the call's stream work is done, every rank's results are in
+ * this rank's copy, with no barrier kernel or collective behind the solve.  Every rank of the group must make the call.
+ */
+int skb_sigkernel_fwd_range(const void* X, const void* Y, int io_dtype,
+                            int A, int B, int M, int N, int D, int dyadic_order,
+                            int static_kind, double static_param, int scheme, int pairs,
+                            long job_lo, long job_hi, double* out, double* const* out_peers, int n_peers,
+                            unsigned long long* const* sig_peers, int my_rank, unsigned long long sig_epoch,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Plugin path: the caller evaluated an arbitrary static kernel itself
  * (any object with Gram_matrix / batch_kernel, static_kernels.py:75-206) and passes the
  * COARSE matrix Ks: (A,B,M,N) for GRAM/SYM, (A,M,N) for BATCH, device fp64.  Second

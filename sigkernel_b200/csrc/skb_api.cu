@@ -358,7 +358,8 @@ size_t skb_bwd_vjp_workspace_bytes(int A, int B, int M, int N, int D, int dyadic
 static int sigkernel_fwd_impl(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
                               int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
                               int arith, double* out, double* const* out_peers, int n_peers, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              size_t workspace_bytes, void* stream, long job_lo = 0, long job_hi = -1,
+                              unsigned long long* const* sig_peers = nullptr, int sig_rank = 0, unsigned long long sig_epoch = 0) {
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, arith);
     if (rc) return rc;
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
@@ -366,7 +367,7 @@ static int sigkernel_fwd_impl(const void* X, const void* Y, int io_dtype, int A,
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
     if (arith != SKB_ARITH_FMA) return SKB_ERR_BAD_ENUM;
     if (!X || !Y || (!out && n_peers == 0)) return SKB_ERR_NULL;
-    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!out_peers || pairs == SKB_PAIRS_SYM))) return SKB_ERR_BAD_ENUM;
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !out_peers)) return SKB_ERR_BAD_ENUM;
     const size_t fixed_bytes = kCounterBytes + align256((size_t)A * M * padded_dim(D) * sizeof(double)) +
                                align256((size_t)B * N * padded_dim(D) * sizeof(double));
     if (!workspace || workspace_bytes < fixed_bytes) return SKB_ERR_WORKSPACE;
@@ -396,6 +397,25 @@ static int sigkernel_fwd_impl(const void* X, const void* Y, int io_dtype, int A,
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     a.njobs = (int)nj;
     a.Dp = Dp; a.D = D;
+    const bool ranged = job_hi >= 0;
+    if (ranged) {
+        // a slice [job_lo, job_hi) of the pair enumeration (one rank's share of a sharded Gram matrix)
+        if (job_lo < 0 || job_hi < job_lo || job_hi > nj) return SKB_ERR_BAD_SHAPE;
+        if (!use5) return SKB_ERR_UNSUPPORTED;
+        if (sig_peers) {
+            if (n_peers <= 0 || sig_rank < 0 || sig_rank >= n_peers || sig_epoch == 0) return SKB_ERR_BAD_ENUM;
+            for (int q = 0; q < n_peers; ++q) {
+                if (!sig_peers[q]) return SKB_ERR_NULL;
+                a.sig_peer[q] = sig_peers[q];
+            }
+            a.sig_rank = sig_rank;
+            a.sig_epoch = sig_epoch;
+            a.n_peer = n_peers;
+        }
+        if (job_hi == job_lo) return sig_peers ? launch_rank_barrier(a, st) : SKB_OK;     // nothing to solve: the barrier alone
+        a.job0 = job_lo;
+        a.njobs = (int)(job_hi - job_lo);
+    }
     if (n_peers > 0) {
         // results go straight to every rank's copy of G: only the fwd5 kernels have that output path
         if (!use5) return SKB_ERR_UNSUPPORTED;
@@ -429,6 +449,16 @@ int skb_sigkernel_fwd_peers(const void* X, const void* Y, int io_dtype, int A, i
     if (n_peers <= 0) return SKB_ERR_BAD_ENUM;
     return sigkernel_fwd_impl(X, Y, io_dtype, A, B, M, N, D, dyadic_order, static_kind, static_param, scheme, pairs, SKB_ARITH_FMA,
                               nullptr, out_peers, n_peers, workspace, workspace_bytes, stream);
+}
+
+int skb_sigkernel_fwd_range(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
+                            int dyadic_order, int static_kind, double static_param, int scheme, int pairs,
+                            long job_lo, long job_hi, double* out, double* const* out_peers, int n_peers,
+                            unsigned long long* const* sig_peers, int my_rank, unsigned long long sig_epoch,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_peers < 0 || job_hi < 0) return SKB_ERR_BAD_ENUM;
+    return sigkernel_fwd_impl(X, Y, io_dtype, A, B, M, N, D, dyadic_order, static_kind, static_param, scheme, pairs, SKB_ARITH_FMA,
+                              out, out_peers, n_peers, workspace, workspace_bytes, stream, job_lo, job_hi, sig_peers, my_rank, sig_epoch);
 }
 
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order, int scheme,

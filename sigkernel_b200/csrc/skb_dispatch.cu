@@ -44,7 +44,7 @@ __global__ void prep2_kernel(const T* __restrict__ X, const T* __restrict__ Y, d
                              double* __restrict__ Xr, double* __restrict__ Yp, double* __restrict__ Yr, long rowsX,
                              long rowsY, int M, int N, int D, int Dp, double cx, double nscale, unsigned int* counter) {
     const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0 && counter) *counter = 0u;
+    if (r == 0 && counter) { counter[0] = 0u; counter[32] = 0u; }   // job queue; finished-block count of the in-kernel rank barrier
     if (r >= rowsX + rowsY) return;
     const bool isx = r < rowsX;
     const long rr = isx ? r : r - rowsX;
@@ -423,6 +423,13 @@ int launch_cond_zero(double* ptr, size_t n, const unsigned int* cond, cudaStream
     size_t blocks = (n + 255) / 256;
     if (blocks > 2048) blocks = 2048;
     cond_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>(ptr, n, cond);
+    return check_launch();
+}
+
+__global__ void rank_barrier_kernel(const KArgs p) { rank_barrier(p); }
+
+int launch_rank_barrier(const KArgs& a, cudaStream_t st) {
+    rank_barrier_kernel<<<1, 1, 0, st>>>(a);
     return check_launch();
 }
 

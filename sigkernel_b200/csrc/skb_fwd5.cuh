@@ -852,8 +852,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     if (p.pairs == PAIRS_SYM) {
                         int a, b;
                         job_decode(p, p.job0 + sjob, a, b);
-                        p.out[(long)a * p.B + b] = res;
-                        p.out[(long)b * p.B + a] = res;
+                        if (p.n_peer > 0) {
+                            // both mirror entries of every rank's copy of G (peer memory)
+                            for (int q = 0; q < p.n_peer; ++q) {
+                                p.out_peer[q][(long)a * p.B + b] = res;
+                                p.out_peer[q][(long)b * p.B + a] = res;
+                            }
+                        } else {
+                            p.out[(long)a * p.B + b] = res;
+                            p.out[(long)b * p.B + a] = res;
+                        }
                     } else if (p.n_peer > 0) {
                         // one 8-byte store per rank: this pair's entry of every rank's copy of G (peer memory)
                         for (int q = 0; q < p.n_peer; ++q) p.out_peer[q][p.job0 + sjob] = res;
@@ -1082,6 +1090,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         } else {
             step(qrun);
             qrun = qrun == 2 ? 0 : qrun + 1;
+        }
+    }
+    if (MODE == 0 && p.sig_epoch != 0ull) {
+        // sharded Gram: the kernel ends with the barrier across the ranks -- the last block to finish (all results of this
+        // rank are then on their way to every copy of G) signals every rank and waits for every rank's signal
+        if (NW > 1) __syncthreads(); else __syncwarp();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(p.counter + 32, 1u);
+            if (prev == gridDim.x - 1) rank_barrier(p);
         }
     }
 }

@@ -48,6 +48,11 @@ struct KArgs {
                                      // index of (min, max); a > b reads the transposed grid: brow <-> bcol)
     unsigned int* flag;              // REV_RECON: set to 1 if a rebuilt grid misses u[., 0] = 1 by more than recon_tol
     double recon_tol;
+    // in-kernel rank barrier of the sharded forward (skb_sigkernel_fwd_range): the last block to finish stores sig_epoch to
+    // slot sig_rank of every rank's signal array (peer memory) and waits until every slot of its own array has reached it
+    unsigned long long* sig_peer[8];
+    int sig_rank;
+    unsigned long long sig_epoch;    // 0: no barrier
     int fbuf_mask;                   // REV_RECON: parked-sum buffers - 1 (a power of two with N * buffers >= 34; skb_fwd5.cuh UFLUSH)
     const unsigned int* cond;        // if non-NULL the kernel returns at once unless *cond != 0 (stored-grid fallback)
     // fused loss head of REV_RECON: gradX[a, m, :] += coef(a,b) * grad_points[a, b, m, :] (atomic), with
@@ -83,6 +88,7 @@ int solver_rows_per_lane(int M, int logd);
 // generic fallback: coarse increments (pairs, M-1, N-1) from a static matrix; static matrix of the fused kinds
 int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, int N, double scale4, bool exact, cudaStream_t st);
 int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double* Ks, cudaStream_t st);
+int launch_rank_barrier(const KArgs& a, cudaStream_t st);      // the in-kernel rank barrier on its own (a rank without pairs)
 // backward on materialised grids (skb_generic_adj.cu)
 int launch_grid_solve(const double* inc, double* U, double* out, long job0, long njobs, int M, int N, int d, bool s1, cudaStream_t st);
 int launch_coarse_sens(const double* U, double* S, long njobs, int M, int N, int d, double scale4, cudaStream_t st);
@@ -167,5 +173,21 @@ int launch_group_tile_rbf(int rc, int logd, int dp2, const TArgs&, cudaStream_t)
 int launch_group_tile_lin(int rc, int logd, int dp2, const TArgs&, cudaStream_t);
 // development / tuning knob (process-wide): 0 = never, 1 = whenever the shape is instantiated, -1 = default heuristic
 void set_tile_mode(int mode);
+
+#ifdef __CUDACC__
+// signal every rank, wait for every rank (one thread; called once every block of the launch has fenced its stores)
+__device__ __forceinline__ void rank_barrier(const KArgs& p) {
+    __threadfence_system();
+    for (int q = 0; q < p.n_peer; ++q)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_peer[q] + p.sig_rank), "l"(p.sig_epoch) : "memory");
+    for (int q = 0; q < p.n_peer; ++q) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.sig_peer[p.sig_rank] + q) : "memory");
+        } while (v < p.sig_epoch);
+    }
+}
+
+#endif
 
 }  // namespace skb

@@ -76,6 +76,47 @@ def sharded_gram(X, Y, gram_fn, group=None, gather=True):
     return torch.cat(parts, dim=0)
 
 
+def sym_tiles(n_rows, world):
+    """Block-cyclic assignment of the upper triangle of a symmetric (n_rows, n_rows) matrix: 2 * world row blocks, the
+    tiles (I, J), I <= J, ordered by diagonal offset and dealt to the ranks round-robin -- every rank gets two diagonal
+    tiles (half the work of a full one) and 2 * world - 1 off-diagonal ones.  (Contiguous row blocks of the triangle would
+    give the first rank about twice the work of the last.)  Returns (row bounds of the blocks, [(I, J, rank), ...])."""
+    nb = max(1, min(2 * world, n_rows))
+    bounds = [row_block(n_rows, i, nb) for i in range(nb)]
+    tiles = []
+    for off in range(nb):
+        for i in range(nb - off):
+            tiles.append((i, i + off, len(tiles) % world))
+    return bounds, tiles
+
+
+def sharded_gram_sym(X, gram_fn, group=None):
+    """G = gram_fn(X, X, sym=True) with the unordered pairs sharded: each rank solves its tiles of the upper triangle
+    (gram_fn(x_I, x_I, True) on the diagonal, gram_fn(x_I, x_J, False) mirrored off it) into a zero matrix; one all-reduce
+    (sum) assembles the full symmetric matrix on every rank.  No gradient flows through it."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    A = X.shape[0]
+    bounds, tiles = sym_tiles(A, world)
+    G = None
+    for I, J, r in tiles:
+        if r != rank:
+            continue
+        (li, hi), (lj, hj) = bounds[I], bounds[J]
+        if hi == li or hj == lj:
+            continue
+        blk = gram_fn(X[li:hi], X[lj:hj], I == J).detach()
+        if G is None:
+            G = torch.zeros((A, A), dtype=blk.dtype, device=blk.device)
+        G[li:hi, lj:hj] = blk
+        if I != J:
+            G[lj:hj, li:hi] = blk.transpose(0, 1)
+    if G is None:
+        G = torch.zeros((A, A), dtype=X.dtype if X.dtype == torch.float64 else torch.float64, device=X.device)
+    dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    return G
+
+
 last_gather = None     # "peers" / "all_gather": which path the last compute_Gram_sharded(gather=True) call took (diagnostic)
 
 
@@ -96,6 +137,14 @@ class _PeerGram:
             self.hdls.append(symm_mem.rendezvous(t, grp))
             self.bufs.append(t)
         self.turn = 0
+        # signal slots of the in-kernel rank barrier (skb_sigkernel_fwd_range): one 64-bit slot per rank, epoch-valued
+        self.sig = symm_mem.empty((64,), dtype=torch.int64, device=device)
+        self.sig.zero_()
+        self.sig_hdl = symm_mem.rendezvous(self.sig, grp)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                      # every rank's slots are zero before anybody signals
+        self.epoch = 0
+        self.rank = dist.get_rank(group)
 
     @classmethod
     def get(cls, n_rows, n_cols, device, group):
@@ -123,26 +172,74 @@ def _gram_into_peers(sig_kernel, X, Y, lo, hi, group):
     except Exception:                                  # symmetric memory unavailable on this system: use the all-gather
         _PeerGram.disabled = True
         return None
+    if ops.lib.skb_forward_plan(X.shape[1], Y.shape[1], X.shape[2], int(sig_kernel.dyadic_order), ops._STATIC[spec[0]],
+                                ops._lib.SCHEME_S1 if sig_kernel._naive_solver else ops._lib.SCHEME_S2) < 4:
+        return None                                    # (decided from the shape alone: every rank takes the same branch)
     k = pg.turn
     pg.turn ^= 1
     hdl, buf = pg.hdls[k], pg.bufs[k]
-    row_bytes = Y.shape[0] * 8
-    ptrs = [int(q) + lo * row_bytes for q in hdl.buffer_ptrs]
-    ok = True
-    if hi > lo:
-        ok = ops.sigkernel_forward_peers(X[lo:hi], Y, spec[0], spec[1], sig_kernel.dyadic_order, ptrs, "gram",
-                                         sig_kernel._naive_solver)
-    if not ok:
-        pg.turn ^= 1
-        return None
-    hdl.barrier(channel=0)                             # every rank's solve (and with it its stores into this copy) is done
+    pg.epoch += 1
+    B = Y.shape[0]
+    # rows [lo, hi) = jobs [lo B, hi B) of the GRAM enumeration; the kernel's last block is the barrier across the ranks
+    ops.sigkernel_forward_range(X, Y, spec[0], spec[1], sig_kernel.dyadic_order, lo * B, hi * B, "gram",
+                                peer_ptrs=[int(q) for q in hdl.buffer_ptrs], naive=sig_kernel._naive_solver,
+                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch))
     return buf
 
 
-def compute_Gram_sharded(sig_kernel, X, Y, group=None, gather=True):
-    """`SigKernel.compute_Gram(X, Y)` sharded over the ranks of `group`.  Differentiable w.r.t. X when the batch
+def _gram_sym_into_peers(sig_kernel, X, group):
+    """Gram(X, X): every rank solves an equal slice of the pairs a <= b (the SYM enumeration of skb_sigkernel_fwd_range) and
+    the solver kernel stores each value -- and its mirror entry -- into every rank's symmetric-memory copy of G.  Returns the
+    local copy or None if this path does not apply (see _gram_into_peers)."""
+    if _PeerGram.disabled or not X.is_cuda or dist.get_backend(group) != "nccl":
+        return None
+    spec = getattr(sig_kernel.static_kernel, "fused_spec", None)
+    spec = spec(True) if spec is not None else None
+    if spec is None or spec[2] is not None or X.dim() != 3 or X.dtype != torch.float64:
+        return None
+    from . import ops
+    A = X.shape[0]
+    try:
+        pg = _PeerGram.get(A, A, X.device, group)
+    except Exception:                                  # symmetric memory unavailable on this system
+        _PeerGram.disabled = True
+        return None
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if ops.lib.skb_forward_plan(X.shape[1], X.shape[1], X.shape[2], int(sig_kernel.dyadic_order), ops._STATIC[spec[0]],
+                                ops._lib.SCHEME_S1 if sig_kernel._naive_solver else ops._lib.SCHEME_S2) < 4:
+        return None
+    total = ops.n_jobs(A, A, "sym")
+    lo, hi = row_block(total, rank, world)
+    k = pg.turn
+    pg.turn ^= 1
+    hdl, buf = pg.hdls[k], pg.bufs[k]
+    pg.epoch += 1
+    ops.sigkernel_forward_range(X, X, spec[0], spec[1], sig_kernel.dyadic_order, lo, hi, "sym",
+                                peer_ptrs=[int(q) for q in hdl.buffer_ptrs], naive=sig_kernel._naive_solver,
+                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch))
+    return buf
+
+
+def compute_Gram_sharded(sig_kernel, X, Y=None, group=None, gather=True, sym=False):
+    """`SigKernel.compute_Gram(X, Y, sym)` sharded over the ranks of `group`.  Differentiable w.r.t. X when the batch
     divides evenly: after `loss(G).backward()` rank r holds d loss / d X in rows [lo_r, hi_r) of `X.grad` (zeros
-    elsewhere); `all_reduce_grad_rows(X.grad)` replicates the full gradient if it is needed everywhere."""
+    elsewhere); `all_reduce_grad_rows(X.grad)` replicates the full gradient if it is needed everywhere.
+
+    sym=True (Y is X): the unordered pairs are sharded instead of the rows -- equal slices of the pair enumeration with
+    peer stores on CUDA / NCCL, block-cyclic tiles of the upper triangle and one all-reduce otherwise (`sym_tiles`) -- so
+    every rank does 1 / world of HALF the square.  Forward values only: with gradients enabled and X requiring them the
+    call takes the row-sharded path of the full square."""
+    if sym:
+        if Y is not None and Y is not X and not (Y.shape == X.shape and torch.equal(Y, X)):
+            raise ValueError("sym=True needs Y = X")
+        if gather and not (torch.is_grad_enabled() and X.requires_grad):
+            G = _gram_sym_into_peers(sig_kernel, X, group)
+            if G is not None:
+                globals()["last_gather"] = "peers_sym"
+                return G
+            globals()["last_gather"] = "all_reduce_sym"
+            return sharded_gram_sym(X, lambda x, y, s: sig_kernel.compute_Gram(x, y, sym=s), group)
+        Y = X
     if gather and X.shape[0] % dist.get_world_size(group) == 0:
         lo, hi = row_block(X.shape[0], dist.get_rank(group), dist.get_world_size(group))
         G = _gram_into_peers(sig_kernel, X, Y, lo, hi, group)

@@ -79,6 +79,49 @@ def sigkernel_forward_peers(X, Y, static_kind, static_param, dyadic_order, peer_
     return True
 
 
+def n_jobs(A, B, pairs):
+    """Length of the pair enumeration of `pairs` (include/sigkernel_b200.h, skb_sigkernel_fwd_range)."""
+    return A if pairs == "batch" else (A * (A + 1) // 2 if pairs == "sym" else A * B)
+
+
+def sigkernel_forward_range(X, Y, static_kind, static_param, dyadic_order, job_lo, job_hi, pairs="gram", out=None,
+                            peer_ptrs=None, naive=False, signal=None):
+    """Jobs [job_lo, job_hi) of the pair enumeration of `pairs` -- one rank's share of a sharded Gram matrix -- written
+    into `out` ((A,B) fp64, other entries untouched) or to every rank's copy (`peer_ptrs`: device pointers to the START of
+    each copy).  'sym' writes both mirror entries.  signal = (pointers to every rank's signal slots, this rank, epoch): the
+    solver kernel ends with the barrier across the ranks (include/sigkernel_b200.h).  Returns False when the shape is
+    outside the kernels with this path."""
+    import ctypes
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    if lib.skb_forward_plan(M, N, D, int(dyadic_order), _STATIC[static_kind], _lib.SCHEME_S1 if naive else _lib.SCHEME_S2) < 4:
+        return False
+    if (out is None) == (peer_ptrs is None):
+        raise ValueError("exactly one of out / peer_ptrs")
+    if out is not None and (out.dtype != torch.float64 or not out.is_contiguous() or out.numel() != (A if pairs == "batch" else A * B)):
+        raise ValueError("out must be a contiguous fp64 tensor laid out like the full result")
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(q) for q in peer_ptrs]) if peer_ptrs is not None else None
+    sarr, srank, sepoch = None, 0, 0
+    if signal is not None:
+        sarr = (ctypes.c_void_p * len(signal[0]))(*[int(q) for q in signal[0]])
+        srank, sepoch = int(signal[1]), int(signal[2])
+    with torch.cuda.device(Xc.device):
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D, int(dyadic_order), _PAIRS[pairs]), Xc.device)
+        rc = lib.skb_sigkernel_fwd_range(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, int(dyadic_order),
+                                         _STATIC[static_kind], float(static_param),
+                                         _lib.SCHEME_S1 if naive else _lib.SCHEME_S2, _PAIRS[pairs], int(job_lo), int(job_hi),
+                                         out.data_ptr() if out is not None else None,
+                                         ctypes.cast(arr, ctypes.c_void_p) if arr is not None else None,
+                                         len(peer_ptrs) if peer_ptrs is not None else 0,
+                                         ctypes.cast(sarr, ctypes.c_void_p) if sarr is not None else None, srank, sepoch,
+                                         ws.data_ptr(), nbytes, _stream())
+        if rc == -4:
+            return False
+        check(rc)
+    return True
+
+
 def sigkernel_forward_from_static(Ks, dyadic_order, pairs="gram", naive=False, exact=False):
     """Plugin path: Ks is the coarse static matrix (A,B,M,N) ('gram'/'sym') or (A,M,N) ('batch')."""
     if not Ks.is_cuda:

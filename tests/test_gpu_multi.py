@@ -49,6 +49,17 @@ def _worker(rank, world, port, q):
         Xr = X[:12].clone().requires_grad_(True)
         sk.compute_Gram(Xr, Y).sum().backward()
         ok.append(bool(torch.allclose(Xg.grad[lo:hi], Xr.grad[lo:hi], rtol=1e-10, atol=1e-12)) and bool((Xg.grad[:lo] == 0).all()))
+        # symmetric Gram: equal slices of the pairs a <= b per rank, both mirror entries stored into every rank's copy
+        for A in (12, 13):
+            Gs = skb.distributed.compute_Gram_sharded(sk, X[:A], sym=True)
+            ref = sk.compute_Gram(X[:A], X[:A], sym=True)
+            ok.append(bool(torch.allclose(Gs, ref, rtol=1e-13, atol=0)) and bool(torch.equal(Gs, Gs.t())))
+            ok.append(skb.distributed.last_gather == "peers_sym")
+        # ... and the block-cyclic tiles + one all-reduce when the peer path is switched off
+        skb.distributed._PeerGram.disabled = True
+        Gs = skb.distributed.compute_Gram_sharded(sk, X, sym=True)
+        ok.append(bool(torch.allclose(Gs, sk.compute_Gram(X, X, sym=True), rtol=1e-13, atol=0)) and skb.distributed.last_gather == "all_reduce_sym")
+        skb.distributed._PeerGram.disabled = False
         q.put((rank, all(ok), path))
     finally:
         dist.destroy_process_group()
