@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr bool XREG = (RC * DP2 <= ((LPP == 16 && R > 8) ? 12 : 8));   // x rows of the pair in registers (the 16-row
                                                                            // strips run 8 warps per SM: room for 12 double2)
     constexpr int LEAD = 4;                      // production column = stencil column + LEAD (mod N)
-    constexpr int RING = 64;                     // job ring depth (lane 0 is < 32 NW steps = RING/2 wraps ahead)
+    constexpr int RING = NW == 1 ? 32 : 64;      // job ring depth (lane 0 is < 32 NW steps = 8 NW wraps < RING/2 ahead; REV_RECON's
+                                                 // flush looks LEAD more steps back)
     if ((MODE == MODE_FWD_STORE || MODE == MODE_REV_GRAD) && p.cond != nullptr) {
         // stored-grid passes queued as the fallback of the reconstruction adjoint: run only if it raised its flag
         if (*reinterpret_cast<const volatile unsigned int*>(p.cond) == 0u) return;

@@ -120,6 +120,45 @@ __global__ void __launch_bounds__(256) fp64_probe_chain_kernel(int iters, double
 }
 }  // namespace skb
 
+namespace skb {
+// Does the fp64 tensor-core path (mma.sync m8n8k4 f64) run beside the DFMA pipe?  OP 20: DMMA only (16 per iteration, 4 chains);
+// OP 21: 16 DFMA + 4 DMMA per iteration; OP 22: 16 DFMA only (reference for 21).  "Instructions" per launch are counted by the caller.
+template <int OP>
+__global__ void __launch_bounds__(256) fp64_probe_dmma_kernel(int iters, double seed, double* sink) {
+    double c[4][2], v[16];
+    const double a = 1.0 + seed * 1e-12, b = seed * 1e-13;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c[i][0] = seed * i; c[i][1] = seed + i; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = seed + (double)(threadIdx.x + i) * 1e-9;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        if (OP == 20) {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = fma(v[i], a, b);
+                if (OP == 21 && (i & 3) == 3)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c[i >> 2][0]), "+d"(c[i >> 2][1]) : "d"(a), "d"(b));
+            }
+        }
+    }
+    double s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s2 += v[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s2 += c[i][0] + c[i][1];
+    if (s2 == 123.456) sink[0] = s2;
+}
+}  // namespace skb
+
 extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, void* stream) {
     using namespace skb;
     if (blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0) return SKB_ERR_BAD_SHAPE;
@@ -135,6 +174,9 @@ extern "C" int skb_fp64_probe(int op, int blocks, int threads, int iters, double
     else if (op == 7) fp64_probe_mix_kernel<7><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 8) fp64_probe_mix_kernel<8><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 9) fp64_probe_mix_kernel<9><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 20) fp64_probe_dmma_kernel<20><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 21) fp64_probe_dmma_kernel<21><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+    else if (op == 22) fp64_probe_dmma_kernel<22><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 10) fp64_probe_chain_kernel<1><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 11) fp64_probe_chain_kernel<2><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
     else if (op == 12) fp64_probe_chain_kernel<4><<<blocks, threads, 0, st>>>(iters, 1.0, sink);
