@@ -79,6 +79,11 @@ void skb_set_tile_mode(int mode);
  * kernels only (round-1 behaviour), 2 = reconstruction with 16 lanes per pair where instantiated. */
 void skb_set_adjoint_mode(int mode);
 
+/* Tuning / test knob (process-wide, default -1): skb_sigkernel_derivatives_from_static.  -1 (or 1) = the streaming kernel
+ * (one warp per pair, FMA-contracted: agrees with the reference's arithmetic to rounding) wherever (M - 1) 2^d <= 256 and
+ * d <= 3, the diagonal kernel elsewhere; 0 = the diagonal kernel always (the reference's operation order, bit for bit). */
+void skb_set_deriv_mode(int mode);
+
 /* Measurement hook (per calling thread): when both are non-NULL, every solver launch made by this thread records
  * `start` immediately before and `stop` immediately after the solver kernel on the launch stream
  * (cudaEvent_t passed as void*), so a caller can time the dominant kernel alone, without the

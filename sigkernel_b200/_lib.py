@@ -32,6 +32,7 @@ SYMBOLS = {
     "skb_sigkernel_bwd_vjp": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _i, _vp, _d, _d, _d, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "skb_gram_weighted_sum": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _i, _vp]),
     "skb_set_profile_events": (None, [_vp, _vp]),
+    "skb_set_deriv_mode": (None, [_i]),
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "skb_forward_plan": (_i, [_i, _i, _i, _i, _i, _i]),
     "skb_adjoint_plan": (_i, [_i, _i, _i, _i, _i, _i]),

@@ -219,6 +219,7 @@ int skb_version(void) { return 2; }
 void skb_set_warps_per_sm(int warps) { set_warps_per_sm(warps); }
 void skb_set_tile_mode(int mode) { set_tile_mode(mode); }
 void skb_set_adjoint_mode(int mode) { set_adjoint_mode(mode); }
+void skb_set_deriv_mode(int mode) { set_deriv_mode(mode); }
 void skb_set_profile_events(void* start_event, void* stop_event) { set_profile_events(start_event, stop_event); }
 
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme) {

@@ -103,6 +103,169 @@ __global__ void deriv_sweep_kernel(const double* __restrict__ inc3, long pairs, 
     }
 }
 
+// ---- streaming variant: one warp per stream of pairs, R fine rows per lane, the lanes one COARSE column apart ----------
+// Lane l owns fine rows [l R, (l+1) R) of every pair of its warp.  Per macro step it computes the R x 2^d cells of one
+// coarse column of its strip from (a) the strip's previous column (registers), (b) the row above, which lane l-1 produced
+// one macro step earlier (shuffles), and (c) the three increments of the coarse cells involved, fetched one macro step
+// ahead.  The pairs of a warp follow each other without draining the wavefront (lane l is l coarse columns behind lane 0,
+// across pair boundaries), so the skew costs 31 macro steps per WARP, not per pair.  No shared memory, no barriers.
+//
+// Arithmetic: the reference's three coupled updates (cuda_backend.py:205-220) with the sums over the three neighbours
+// factored out.  With q = inc/4, S = k01 + k10 + k00, T = S + k, Sd = k01' + k10' + k00', V = Sd + k':
+//     k   = (k01 + k10) a - k00 b
+//     k'  = (1 + 2q)(k01' + k10') + (q inc - 1) k00' + (inc'/4) T + (q inc') k00
+//     k'' = (1 + 2q)(k01'' + k10'') + (q inc - 1) k00'' + (inc''/4) T + (inc'/2) V + (q inc'') k00 + (inc inc'/2) k00'
+// -- 19 DP instructions per cell instead of the 62 of the statement-by-statement form; the results agree with it to
+// rounding (1e-13 relative), not bit for bit.  Covers (len_x - 1) 2^d <= 256 at dyadic order <= 3.
+template <int R, int LOGD>
+__global__ void __launch_bounds__(128, 2) deriv_stream_kernel(const double* __restrict__ inc3, long pairs, int Mc, int Nc,
+                                                              double* __restrict__ out) {
+    constexpr int F = 1 << LOGD;
+    constexpr int NCR = R >= F ? R / F : 1;       // coarse rows of a lane's strip
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    if (warp >= pairs) return;
+    const long P = (pairs - warp + nwarps - 1) / nwarps;      // pairs of this warp: warp, warp + nwarps, ...
+    const int MM = Mc << LOGD;
+    const int crow0 = (lane * R) >> LOGD;         // first coarse row of the strip
+    const int olane = (MM - 1) / R, orow = (MM - 1) % R;   // owner of the last grid row
+    const long cell3 = (long)Mc * Nc * 3;
+
+    double k[R], kd[R], kdd[R];                   // the strip's values at the last fine column computed
+    double tpv = 1.0, tpvd = 0.0, tpvdd = 0.0;    // row above the strip at that column
+    double bot[F], botd[F], botdd[F];             // bottom row of the strip over the coarse column just computed
+#pragma unroll
+    for (int r = 0; r < R; ++r) { k[r] = 1.0; kd[r] = 0.0; kdd[r] = 0.0; }
+#pragma unroll
+    for (int f = 0; f < F; ++f) { bot[f] = 1.0; botd[f] = 0.0; botdd[f] = 0.0; }
+    // increments of the coarse cells (this lane's coarse rows) x (the coarse column of the NEXT macro step)
+    double ni[NCR], nid[NCR], nidd[NCR];
+    auto fetch = [&](long pi, int jc) {
+        // pi-th pair of the warp, coarse column jc; out of range (before the first / past the last pair): zeros
+#pragma unroll
+        for (int c = 0; c < NCR; ++c) {
+            const int cr = crow0 + c;
+            const bool ok = pi >= 0 && pi < P && cr < Mc;
+            const double* q = inc3 + (ok ? (warp + pi * nwarps) * cell3 + ((long)cr * Nc + jc) * 3 : 0);
+            ni[c] = ok ? __ldg(q) : 0.0;
+            nid[c] = ok ? __ldg(q + 1) : 0.0;
+            nidd[c] = ok ? __ldg(q + 2) : 0.0;
+        }
+    };
+    // lane l starts l macro steps late: (pi, jc) = position of the NEXT macro step of this lane in its stream of pairs
+    long pi = 0;                                  // (negative: before the first pair)
+    int jc = 0;                                   // counts up to Nc, then the next pair begins
+    if (lane > 0) { pi = -((lane - 1) / Nc + 1); jc = (int)(((long)Nc * (-pi)) - lane); }
+    fetch(pi, jc);
+    const long steps = P * Nc + 31;
+    for (long s = 0; s < steps; ++s) {
+        // row above: what lane - 1 produced one macro step ago (same pair, same coarse column); boundary for lane 0
+        double top[F], topd[F], topdd[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            top[f] = __shfl_up_sync(FULL, bot[f], 1);
+            topd[f] = __shfl_up_sync(FULL, botd[f], 1);
+            topdd[f] = __shfl_up_sync(FULL, botdd[f], 1);
+            if (lane == 0) { top[f] = 1.0; topd[f] = 0.0; topdd[f] = 0.0; }
+        }
+        // this macro step's increments (fetched one step ago) -> per-coarse-cell constants; fetch the next step's
+        double ca[NCR], cnb[NCR], A1[NCR], A2[NCR], qd[NCR], c1[NCR], qdd[NCR], hh[NCR], c3[NCR], c4[NCR];
+#pragma unroll
+        for (int c = 0; c < NCR; ++c) {
+            const double inc = ni[c], incd = nid[c], incdd = nidd[c];
+            const double e12 = inc * inc * (1.0 / 12), q = 0.25 * inc;
+            ca[c] = (1.0 + 0.5 * inc) + e12;
+            cnb[c] = e12 - 1.0;
+            A1[c] = 1.0 + 0.5 * inc;
+            A2[c] = fma(q, inc, -1.0);
+            qd[c] = 0.25 * incd;
+            c1[c] = q * incd;
+            qdd[c] = 0.25 * incdd;
+            hh[c] = 0.5 * incd;
+            c3[c] = q * incdd;
+            c4[c] = 0.5 * inc * incd;
+        }
+        const bool active = pi >= 0 && pi < P;
+        const long pi_now = pi;
+        const int jc_now = jc;
+        if (++jc == Nc) { jc = 0; ++pi; }
+        fetch(pi, jc);
+        if (active) {
+            if (jc_now == 0) {
+                // a new pair: boundary column
+#pragma unroll
+                for (int r = 0; r < R; ++r) { k[r] = 1.0; kd[r] = 0.0; kdd[r] = 0.0; }
+                tpv = 1.0; tpvd = 0.0; tpvdd = 0.0;
+            }
+            double up[F], upd[F], updd[F];        // the row above the one being computed, over this coarse column
+#pragma unroll
+            for (int f = 0; f < F; ++f) { up[f] = top[f]; upd[f] = topd[f]; updd[f] = topdd[f]; }
+            double dg0 = tpv, dg0d = tpvd, dg0dd = tpvdd;     // its value one fine column to the left
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int c = R >= F ? r >> LOGD : 0;
+                double lk = k[r], ld = kd[r], ldd = kdd[r];   // cell to the left
+                double dk = dg0, dd = dg0d, ddd = dg0dd;       // diagonal cell
+                const double nl = lk, nld = ld, nldd = ldd;    // (becomes the next row's first diagonal)
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    const double uk = up[f], ud = upd[f], udd = updd[f];
+                    const double s0 = uk + lk;
+                    const double kn = fma(s0, ca[c], cnb[c] * dk);
+                    const double T = (s0 + dk) + kn;
+                    const double sd0 = ud + ld;
+                    const double kdn = fma(A1[c], sd0, fma(A2[c], dd, fma(qd[c], T, c1[c] * dk)));
+                    const double V = (sd0 + dd) + kdn;
+                    const double sdd0 = udd + ldd;
+                    const double kddn = fma(A1[c], sdd0, fma(A2[c], ddd, fma(qdd[c], T, fma(hh[c], V, fma(c3[c], dk, c4[c] * dd)))));
+                    dk = uk; dd = ud; ddd = udd;               // this cell's "up" is the next cell's diagonal
+                    lk = kn; ld = kdn; ldd = kddn;
+                    up[f] = kn; upd[f] = kdn; updd[f] = kddn;  // and this row is the next row's "up"
+                }
+                k[r] = lk; kd[r] = ld; kdd[r] = ldd;
+                dg0 = nl; dg0d = nld; dg0dd = nldd;
+            }
+            tpv = top[F - 1]; tpvd = topd[F - 1]; tpvdd = topdd[F - 1];
+#pragma unroll
+            for (int f = 0; f < F; ++f) { bot[f] = up[f]; botd[f] = upd[f]; botdd[f] = updd[f]; }
+            if (jc_now == Nc - 1 && lane == olane) {
+                const long pair = warp + pi_now * nwarps;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r == orow) {
+                        out[pair * 3 + 0] = k[r];
+                        out[pair * 3 + 1] = kd[r];
+                        out[pair * 3 + 2] = kdd[r];
+                    }
+            }
+        }
+    }
+}
+
+static int g_deriv_mode = -1;                     // 0: the diagonal kernel (bit-exact) always; else streaming where it applies
+void set_deriv_mode(int mode) { g_deriv_mode = mode; }
+
+template <int R>
+static int launch_deriv_stream_r(const double* inc3, long pairs, int Mc, int Nc, int d, double* out3, cudaStream_t st) {
+    long warps = pairs;
+    const long cap = (long)sm_count() * 8;       // two blocks of four warps per SM (the 8-row strips take ~250 registers)
+    if (warps > cap) warps = cap;
+    const unsigned blocks = (unsigned)((warps + 3) / 4);
+    switch (d) {
+        case 0: deriv_stream_kernel<R, 0><<<blocks, 128, 0, st>>>(inc3, pairs, Mc, Nc, out3); break;
+        case 1: deriv_stream_kernel<R, 1><<<blocks, 128, 0, st>>>(inc3, pairs, Mc, Nc, out3); break;
+        case 2: deriv_stream_kernel<R, 2><<<blocks, 128, 0, st>>>(inc3, pairs, Mc, Nc, out3); break;
+        case 3: deriv_stream_kernel<R, 3><<<blocks, 128, 0, st>>>(inc3, pairs, Mc, Nc, out3); break;
+        default: return SKB_ERR_UNSUPPORTED;
+    }
+    return check_launch();
+}
+
+bool deriv_stream_applies(int M, int d) {
+    return g_deriv_mode != 0 && d <= 3 && ((long)(M - 1) << d) <= 256;
+}
+
 int launch_derivatives(const double* K0, const double* K1, const double* K2, long pairs, int M, int N, int d,
                        double eps, double* inc3, double* out3, cudaStream_t st) {
     const long cells = pairs * (long)(M - 1) * (N - 1);
@@ -112,6 +275,13 @@ int launch_derivatives(const double* K0, const double* K1, const double* K2, lon
     int rc = check_launch();
     if (rc) return rc;
     const long MM = (long)(M - 1) << d;
+    if (deriv_stream_applies(M, d)) {
+        const int rows = (int)((MM + 31) / 32);
+        if (rows <= 1) return launch_deriv_stream_r<1>(inc3, pairs, M - 1, N - 1, d, out3, st);
+        if (rows <= 2) return launch_deriv_stream_r<2>(inc3, pairs, M - 1, N - 1, d, out3, st);
+        if (rows <= 4) return launch_deriv_stream_r<4>(inc3, pairs, M - 1, N - 1, d, out3, st);
+        return launch_deriv_stream_r<8>(inc3, pairs, M - 1, N - 1, d, out3, st);
+    }
     const size_t smem = (size_t)9 * (MM + 1) * sizeof(double);
     if (smem > 200 * 1024) return SKB_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {

@@ -56,9 +56,33 @@ def test_derivatives_bitwise_from_static(skb, O, A, B, M, N, D, d, static):
     sk = O.RBFKernel(0.7) if static == "rbf" else O.LinearKernel(1.0)
     K0, K1, K2 = sk.Gram_matrix(X, Y), sk.Gram_matrix(X + eps * gamma, Y), sk.Gram_matrix(X + 2. * eps * gamma, Y)
     ref = O.compute_kernel_and_derivatives_Gram(X, Y, gamma, sk, d, eps)
-    got = skb.ops.kernel_and_derivatives_from_static(K0.cuda(), K1.cuda(), K2.cuda(), d, eps)
+    skb._lib.lib.skb_set_deriv_mode(0)           # the diagonal kernel: the reference's operation order
+    try:
+        got = skb.ops.kernel_and_derivatives_from_static(K0.cuda(), K1.cuda(), K2.cuda(), d, eps)
+    finally:
+        skb._lib.lib.skb_set_deriv_mode(-1)
     for r, g in zip(ref, got):
         assert np.array_equal(g.cpu().numpy(), r.numpy())
+    # default dispatch (the streaming kernel up to 256 fine rows): same algebra, sums factored and FMA-contracted
+    got = skb.ops.kernel_and_derivatives_from_static(K0.cuda(), K1.cuda(), K2.cuda(), d, eps)
+    for r, g in zip(ref, got):
+        assert fwd_err(g.cpu().numpy(), r.numpy()) <= 1e-11
+
+
+@pytest.mark.parametrize("A,B,M,N,D,d", [(5, 3, 64, 64, 3, 2), (2, 2, 33, 9, 2, 3), (3, 3, 257, 5, 2, 0), (2, 3, 129, 40, 4, 1),
+                                         (2, 2, 6, 70, 2, 2), (1, 2, 40, 3, 2, 1)])
+def test_streaming_derivative_kernel_vs_oracle(skb, O, A, B, M, N, D, d):
+    """Every strip height (1, 2, 4, 8 rows per lane) and dyadic order of the streaming kernel against the oracle."""
+    X = make_paths("bm", 60 + M, (A, M, D))
+    Y = make_paths("bm", 61 + N, (B, N, D))
+    gamma = make_paths("rand", 62, (A, M, D))
+    eps = 1e-4
+    sk = O.RBFKernel(0.9)
+    K0, K1, K2 = sk.Gram_matrix(X, Y), sk.Gram_matrix(X + eps * gamma, Y), sk.Gram_matrix(X + 2. * eps * gamma, Y)
+    ref = O.compute_kernel_and_derivatives_Gram(X, Y, gamma, sk, d, eps)
+    got = skb.ops.kernel_and_derivatives_from_static(K0.cuda(), K1.cuda(), K2.cuda(), d, eps)
+    for r, g in zip(ref, got):
+        assert fwd_err(g.cpu().numpy(), r.numpy()) <= 1e-11
 
 
 def test_derivative_is_the_eps_derivative_of_the_kernel(skb):
