@@ -167,6 +167,16 @@ int skb_sigkernel_fwd_peers(const void* X, const void* Y, int io_dtype,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The static kernel matrix itself: Ks[pair][i][j] = kappa(X_a[i], Y_b[j]) (fp64; (A,B,M,N) for GRAM, (A,M,N) for BATCH) for
+ * the two built-in kernels (static_kernels.py:17-33 Linear, :42-73 RBF) -- what the reference's plugin interface
+ * (`Gram_matrix` / `batch_kernel`) returns, in one pass over the output.  Used by the derivative path, which needs the
+ * matrices of three perturbed copies of X (sigkernel.py:524-539).  Workspace: skb_fwd_workspace_bytes (prepared paths).
+ */
+int skb_static_gram(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D,
+                    int static_kind, double static_param, int pairs, double* Ks,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * One slice [job_lo, job_hi) of the pair enumeration of `pairs` -- a rank's share of a sharded Gram matrix.  GRAM: job =
  * a * B + b; BATCH: job = a; SYM: the pairs a <= b, row by row (job = a * A - a (a - 1) / 2 + (b - a)) -- equal slices of
  * the SYM enumeration are equal amounts of work, which contiguous row blocks of a symmetric matrix are not.

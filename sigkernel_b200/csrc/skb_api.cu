@@ -462,6 +462,30 @@ int skb_sigkernel_fwd_range(const void* X, const void* Y, int io_dtype, int A, i
                               out, out_peers, n_peers, workspace, workspace_bytes, stream, job_lo, job_hi, sig_peers, my_rank, sig_epoch);
 }
 
+int skb_static_gram(const void* X, const void* Y, int io_dtype, int A, int B, int M, int N, int D, int static_kind,
+                    double static_param, int pairs, double* Ks, void* workspace, size_t workspace_bytes, void* stream) {
+    if (A <= 0 || B <= 0 || M < 1 || N < 1 || D <= 0) return SKB_ERR_BAD_SHAPE;
+    if (pairs != SKB_PAIRS_GRAM && pairs != SKB_PAIRS_BATCH) return SKB_ERR_BAD_ENUM;
+    if (pairs == SKB_PAIRS_BATCH && A != B) return SKB_ERR_BAD_SHAPE;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
+    if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
+    if (!X || !Y || !Ks) return SKB_ERR_NULL;
+    const int Dp = padded_dim(D);
+    const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
+    if (!workspace || workspace_bytes < kCounterBytes + xb + yb) return SKB_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    double* Xp = (double*)(w + kCounterBytes);
+    double* Yp = (double*)(w + kCounterBytes + xb);
+    double cx, nsc;
+    prep_factors(static_kind, static_param, cx, nsc);
+    int rc = launch_prep2(X, Y, io_dtype, Xp, nullptr, Yp, nullptr, A, M, B, N, D, Dp, cx, nsc, nullptr, st);
+    if (rc) return rc;
+    KArgs a = base_args(A, B, M, N, 0, SKB_SCHEME_S2, pairs);
+    a.Xp = Xp; a.Yp = Yp; a.Dp = Dp; a.D = D;
+    return launch_static_matrix(a, static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, 0, njobs_of(A, B, pairs), Ks, st);
+}
+
 int skb_sigkernel_fwd_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order, int scheme,
                                   int pairs, int arith, double* out, void* workspace, size_t workspace_bytes,
                                   void* stream) {

@@ -79,6 +79,19 @@ def sigkernel_forward_peers(X, Y, static_kind, static_param, dyadic_order, peer_
     return True
 
 
+def static_gram(X, Y, static_kind, static_param, pairs="gram"):
+    """kappa(X_a[i], Y_b[j]) for the two built-in static kernels: (A,B,M,N) fp64 ('gram') or (A,M,N) ('batch')."""
+    Xc, Yc, dt = _io(X, Y)
+    A, M, D = Xc.shape
+    B, N, _ = Yc.shape
+    with torch.cuda.device(Xc.device):
+        Ks = torch.empty((A, M, N) if pairs == "batch" else (A, B, M, N), dtype=torch.float64, device=Xc.device)
+        ws, nbytes = _workspace(lib.skb_fwd_workspace_bytes(A, B, M, N, D, 0, _PAIRS[pairs]), Xc.device)
+        check(lib.skb_static_gram(Xc.data_ptr(), Yc.data_ptr(), dt, A, B, M, N, D, _STATIC[static_kind], float(static_param),
+                                  _PAIRS[pairs], Ks.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+    return Ks
+
+
 def n_jobs(A, B, pairs):
     """Length of the pair enumeration of `pairs` (include/sigkernel_b200.h, skb_sigkernel_fwd_range)."""
     return A if pairs == "batch" else (A * (A + 1) // 2 if pairs == "sym" else A * B)

@@ -422,9 +422,15 @@ def k_kgrad(X, Y, gamma, dyadic_order, static_kernel, eps=1e-4):
     reference does (:524-539); the finite differences in eps, the second differences, the dyadic refinement
     and the three coupled PDE stencils (cuda_backend.py:165-223) run in one CUDA kernel pair."""
     with torch.no_grad():
-        K0 = static_kernel.Gram_matrix(X, Y)
-        K1 = static_kernel.Gram_matrix(X + eps * gamma, Y)
-        K2 = static_kernel.Gram_matrix(X + 2. * eps * gamma, Y)
+        spec = _fused(static_kernel, gram=True)
+        if spec is not None and spec[2] is None and X.is_cuda and X.dim() == 3:
+            # the two built-in kernels: one CUDA pass per static matrix instead of the plugin's chain of torch ops
+            gram = lambda x: ops.static_gram(x, Y, spec[0], spec[1], "gram")
+        else:
+            gram = lambda x: static_kernel.Gram_matrix(x, Y)
+        K0 = gram(X)
+        K1 = gram(X + eps * gamma)
+        K2 = gram(X + 2. * eps * gamma)
         K, Kd, Kdd = ops.kernel_and_derivatives_from_static(K0, K1, K2, dyadic_order, eps)
     return K.to(X.dtype), Kd.to(X.dtype), Kdd.to(X.dtype)
 
