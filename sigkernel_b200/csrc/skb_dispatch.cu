@@ -429,7 +429,7 @@ int launch_cond_zero(double* ptr, size_t n, const unsigned int* cond, cudaStream
 __global__ void rank_barrier_kernel(const KArgs p) { rank_barrier(p); }
 
 int launch_rank_barrier(const KArgs& a, cudaStream_t st) {
-    rank_barrier_kernel<<<1, 1, 0, st>>>(a);
+    rank_barrier_kernel<<<1, 32, 0, st>>>(a);
     return check_launch();
 }
 

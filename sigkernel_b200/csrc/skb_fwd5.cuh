@@ -1097,9 +1097,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         // sharded Gram: the kernel ends with the barrier across the ranks -- the last block to finish (all results of this
         // rank are then on their way to every copy of G) signals every rank and waits for every rank's signal
         if (NW > 1) __syncthreads(); else __syncwarp();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned prev = atomicAdd(p.counter + 32, 1u);
+        if (threadIdx.x < 32) {
+            unsigned prev = 0u;
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                prev = atomicAdd(p.counter + 32, 1u);
+            }
+            prev = __shfl_sync(FULL, prev, 0);
             if (prev == gridDim.x - 1) rank_barrier(p);
         }
     }

@@ -176,17 +176,19 @@ int launch_group_tile_lin(int rc, int logd, int dp2, const TArgs&, cudaStream_t)
 void set_tile_mode(int mode);
 
 #ifdef __CUDACC__
-// signal every rank, wait for every rank (one thread; called once every block of the launch has fenced its stores)
+// signal every rank, wait for every rank: lane q of the calling warp takes rank q (called by a full warp once every block
+// of the launch has fenced its stores)
 __device__ __forceinline__ void rank_barrier(const KArgs& p) {
     __threadfence_system();
-    for (int q = 0; q < p.n_peer; ++q)
+    const int q = threadIdx.x & 31;
+    if (q < p.n_peer) {
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.sig_peer[q] + p.sig_rank), "l"(p.sig_epoch) : "memory");
-    for (int q = 0; q < p.n_peer; ++q) {
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.sig_peer[p.sig_rank] + q) : "memory");
         } while (v < p.sig_epoch);
     }
+    __syncwarp();
 }
 
 #endif

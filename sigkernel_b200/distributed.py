@@ -117,6 +117,12 @@ def sharded_gram_sym(X, gram_fn, group=None):
     return G
 
 
+# how the ranks synchronise after a peer-store solve: "handle" = a symmetric-memory barrier kernel behind the solve,
+# "kernel" = the solver kernel's last block signals and waits itself (skb_sigkernel_fwd_range).  Measured on B200 (DESIGN.md
+# 5): no difference beyond run-to-run noise at 2 ranks (0.37 ms per step either way), the separate barrier is faster at 8
+# (0.372 vs 0.385 ms) -- the default.
+RANK_BARRIER = __import__("os").environ.get("SKB_RANK_BARRIER", "handle")
+
 last_gather = None     # "peers" / "all_gather": which path the last compute_Gram_sharded(gather=True) call took (diagnostic)
 
 
@@ -181,9 +187,12 @@ def _gram_into_peers(sig_kernel, X, Y, lo, hi, group):
     pg.epoch += 1
     B = Y.shape[0]
     # rows [lo, hi) = jobs [lo B, hi B) of the GRAM enumeration; the kernel's last block is the barrier across the ranks
+    in_kernel = RANK_BARRIER == "kernel"
     ops.sigkernel_forward_range(X, Y, spec[0], spec[1], sig_kernel.dyadic_order, lo * B, hi * B, "gram",
                                 peer_ptrs=[int(q) for q in hdl.buffer_ptrs], naive=sig_kernel._naive_solver,
-                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch))
+                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch) if in_kernel else None)
+    if not in_kernel:
+        hdl.barrier(channel=0)
     return buf
 
 
@@ -214,9 +223,12 @@ def _gram_sym_into_peers(sig_kernel, X, group):
     pg.turn ^= 1
     hdl, buf = pg.hdls[k], pg.bufs[k]
     pg.epoch += 1
+    in_kernel = RANK_BARRIER == "kernel"
     ops.sigkernel_forward_range(X, X, spec[0], spec[1], sig_kernel.dyadic_order, lo, hi, "sym",
                                 peer_ptrs=[int(q) for q in hdl.buffer_ptrs], naive=sig_kernel._naive_solver,
-                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch))
+                                signal=([int(q) for q in pg.sig_hdl.buffer_ptrs], pg.rank, pg.epoch) if in_kernel else None)
+    if not in_kernel:
+        hdl.barrier(channel=0)
     return buf
 
 
