@@ -76,7 +76,8 @@ void skb_set_tile_mode(int mode);
 
 /* Tuning / test knob (process-wide, default -1): which kernels serve the backward entry points.  -1 (or 1) = adjoint by
  * reconstruction (32 lanes per pair) with the stored-grid kernels queued as a device-side fallback, 0 = stored-grid
- * kernels only (round-1 behaviour), 2 = reconstruction with 16 lanes per pair where instantiated. */
+ * kernels only (round-1 behaviour), 2 = reconstruction with 16 lanes per pair where instantiated, 3 = as -1 but without
+ * the unordered-pair sweep of Gram(X, X) (skb_adjoint_sym_supported returns 0). */
 void skb_set_adjoint_mode(int mode);
 
 /* Tuning / test knob (process-wide, default -1): skb_sigkernel_derivatives_from_static.  -1 (or 1) = the streaming kernel
@@ -110,6 +111,9 @@ int skb_fp64_probe(int op, int blocks, int threads, int iters, double* sink, voi
  * Negative values are SKB_ERR_* codes for bad arguments. */
 int skb_forward_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
 int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int scheme);
+/* 1 if skb_sigkernel_bwd_vjp takes pairs = SKB_PAIRS_SYM for paths of this length (Gram(X, X): one reversed sweep per
+ * unordered pair yields the gradient w.r.t. both paths), else 0. */
+int skb_adjoint_sym_supported(int M, int D, int dyadic_order, int static_kind, int scheme);
 
 /* ---- workspaces -------------------------------------------------------------------
  * Every compute entry point takes a caller-owned device scratch buffer (256-byte aligned) that
@@ -253,7 +257,13 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
  *                         carries the reference's factor 2 for Gram(X, X) (sigkernel.py:410-412), out_scale_dev (device,
  *                         may be NULL) the upstream gradient of a scalar loss.  g is summed with fp64 atomics (the order
  *                         over b varies from run to run).  grad_points (pairs, M, D) is also written if not NULL; one of
- *                         gradX (A, M, D) and grad_points must be given.  Workspace: skb_bwd_vjp_workspace_bytes (smaller is accepted: without room for
+ *                         gradX (A, M, D) and grad_points must be given.  pairs = SKB_PAIRS_SYM (Y = X, ctx_pairs = SYM, loss-head
+ *                         weights only, gradX only; skb_adjoint_sym_supported): ONE sweep per unordered pair a <= b --
+ *                         the same sensitivities are also contracted with the rows of X_a per node column, which gives
+ *                         d k / d X_b (cython_backend.pyx:76-97 solves the triangle only in the forward; here the backward
+ *                         does too) --
+ *                             g[c] = sum over ORDERED pairs (a, b) of coef(a, b) d k(X_a, X_b) / d X_c   (both arguments),
+ *                         half the sweeps of the GRAM call with out_scale 2 that it replaces.  Workspace: skb_bwd_vjp_workspace_bytes (smaller is accepted: without room for
  *                         one pair's grid + gradients the stored-grid fallback is not queued; the flag word at byte 64 of
  *                         the workspace is then the caller's to check -- non-zero = a rebuilt grid missed its boundary
  *                         by more than 1e-10 and the result should be recomputed with skb_sigkernel_fwd_bwd).

@@ -36,6 +36,7 @@ SYMBOLS = {
     "skb_fp64_probe": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "skb_forward_plan": (_i, [_i, _i, _i, _i, _i, _i]),
     "skb_adjoint_plan": (_i, [_i, _i, _i, _i, _i, _i]),
+    "skb_adjoint_sym_supported": (_i, [_i, _i, _i, _i, _i]),
     "skb_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_sigkernel_fwd_peers": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _vp, _i, _vp, _sz, _vp]),

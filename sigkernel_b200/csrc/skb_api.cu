@@ -6,7 +6,8 @@
 
 namespace skb {
 
-constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5;
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5,
+              MODE_REV_RECON_SYM = 6;
 
 static thread_local int g_last_cuda = 0;
 
@@ -243,6 +244,14 @@ int skb_adjoint_plan(int M, int N, int D, int dyadic_order, int static_kind, int
     if (recon5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1)) return 6;
     if (solver_rows_per_lane(M, dyadic_order) < 0) return 7;      // materialised grids (skb_generic_adj.cu): any length
     return adjoint5_applies(kind, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1) ? 5 : 1;
+}
+
+int skb_adjoint_sym_supported(int M, int D, int dyadic_order, int static_kind, int scheme) {
+    if (M < 2 || D <= 0 || dyadic_order < 0 || dyadic_order > 20) return 0;
+    if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return 0;
+    const int kind = static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR;
+    return recon5_applies(kind, M, M, D, dyadic_order, scheme == SKB_SCHEME_S1) &&
+           recon5_sym_applies(kind, M, M, D, dyadic_order, scheme == SKB_SCHEME_S1) ? 1 : 0;
 }
 
 size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_order, int pairs) {
@@ -693,16 +702,21 @@ int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype, int A, int
                           void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
     if (rc) return rc;
-    if (pairs == SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;          // the reversed sweep runs over every ordered pair
+    // pairs = SYM (Gram(X, X), Y = X): ONE reversed sweep per unordered pair a <= b yields both d k / d X_a and d k / d X_b
+    // (MODE_REV_RECON_SYM); loss-head weights only, no per-pair output
+    const bool usym = pairs == SKB_PAIRS_SYM;
+    if (usym && (ctx_pairs != SKB_PAIRS_SYM || A != B || M != N || grad_out || grad_points || !gradX)) return SKB_ERR_BAD_ENUM;
     if (ctx_pairs != pairs && !(ctx_pairs == SKB_PAIRS_SYM && pairs == SKB_PAIRS_GRAM && A == B && M == N)) return SKB_ERR_BAD_ENUM;
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
     if (!X || !Y || !ctx || (!gradX && !grad_points)) return SKB_ERR_NULL;
     if (!recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme)) return SKB_ERR_UNSUPPORTED;
+    if (usym && !recon5_sym_applies(static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1))
+        return SKB_ERR_UNSUPPORTED;
     const int Dp = padded_dim(D);
     const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
-    const long nj = njobs_of(A, B, pairs);
+    const long nj = njobs_of(A, B, usym ? SKB_PAIRS_GRAM : pairs);      // (sizes the fallback's part of the workspace)
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
     const size_t kb = align256((size_t)nj * sizeof(double));
     const size_t gb = align256((size_t)A * M * D * sizeof(double));       // gradient of this call before scaling / accumulation
@@ -735,25 +749,28 @@ int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype, int A, int
     if (rc) return rc;
     KArgs ra = base_args(A, B, M, N, dyadic_order, scheme, pairs);
     ra.Xp = Xr; ra.Yp = Yr; ra.counter = counter; ra.Dp = Dp; ra.D = D;
-    ra.njobs = (int)nj;
+    ra.njobs = (int)njobs_of(A, B, pairs);
     ra.counter_clean = 1;
     ra.grad = grad_points;
     ra.gscale = static_kind == SKB_STATIC_RBF ? 2.0 / static_param : static_param;
     set_ctx(ra, const_cast<void*>(ctx), njobs_of(A, B, ctx_pairs), M, N, dyadic_order);
     ra.bsym = ctx_pairs == SKB_PAIRS_SYM && pairs != SKB_PAIRS_SYM;
     ra.flag = flag; ra.recon_tol = kReconTol;
-    ra.gout = grad_out; ra.gradX = gradX ? gtmp : nullptr; ra.w_diag = w_diag; ra.w_off = w_off;
-    rc = launch_recon5(MODE_REV_RECON, kind5, dyadic_order, ra, st);
+    // unordered pairs: sum over the ORDERED pairs of coef (a, b) d k(X_a, X_b) / d X = for a < b twice the weight on the one
+    // sweep that stands for (a, b) and (b, a); the diagonal pair's sweep already yields both of its terms
+    ra.gout = grad_out; ra.gradX = gradX ? gtmp : nullptr; ra.w_diag = w_diag; ra.w_off = usym ? 2.0 * w_off : w_off;
+    rc = launch_recon5(usym ? MODE_REV_RECON_SYM : MODE_REV_RECON, kind5, dyadic_order, ra, st);
     if (rc) return rc;
     if (!fallback) return gradX ? launch_combine(gradX, gtmp, (size_t)A * M * D, out_scale, out_scale_dev, accumulate, st) : SKB_OK;
     // stored-grid fallback behind a device-side test of the flag: forward with store, reversed sweep, loss head
-    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
+    // (unordered pairs: the fallback runs over the full square with only d / d first argument -- twice the weights)
+    KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, usym ? SKB_PAIRS_GRAM : pairs);
     fa.Xp = Xp; fa.Yp = Yp; fa.out = (double*)(w + fixed); fa.counter = counter; fa.Dp = Dp; fa.D = D;
     KArgs rb = fa;
     rb.Xp = Xr; rb.Yp = Yr; rb.out = nullptr; rb.grad = grad_points;
     rb.gscale = ra.gscale;
     fa.cond = rb.cond = flag;
-    VjpOpts vo = {grad_out, w_diag, w_off, gtmp};
+    VjpOpts vo = {grad_out, usym ? 2.0 * w_diag : w_diag, usym ? 2.0 * w_off : w_off, gtmp};
     if (gradX) {
         rc = launch_cond_zero(gtmp, (size_t)A * M * D, flag, st);
         if (rc) return rc;

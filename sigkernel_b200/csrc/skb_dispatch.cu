@@ -327,6 +327,13 @@ static int pow2_ceil(int v) {
 static int recon5_plan(int mode, int M, int logd, int* rc_out, int* lpp_out) {
     if (logd > 3) return 0;
     const int rmax = 8 >> logd;
+    if (mode == MODE_REV_RECON_SYM) {
+        // the unordered-pair sweep: one warp of 32 lanes per pair only
+        const int rc = pow2_ceil((M + 31) / 32);
+        *lpp_out = 32;
+        *rc_out = rc;
+        return rc <= rmax ? 1 : 0;
+    }
     // 16 lanes per pair (two pair streams per warp) wherever the strip is instantiated: the forward pass always, the
     // reversed sweep only on request (mode 2; measured at 128 x 128 pairs of 64 points, dyadic order 1: 0.71 ms with 32
     // lanes per pair, 0.89 ms with 16 -- twice the rows per lane do not pay for the larger, slower step there)
@@ -353,6 +360,17 @@ static int recon5_plan(int mode, int M, int logd, int* rc_out, int* lpp_out) {
             }
     }
     return 0;
+}
+
+// the unordered-pair sweep of Gram(X, X) (MODE_REV_RECON_SYM): single-warp strips with register accumulators
+bool recon5_sym_applies(int kind, int M, int N, int D, int logd, bool s1) {
+    if (g_adjoint_mode == 0 || g_adjoint_mode == 3 || s1 || N < 4 || M != N) return false;
+    if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
+    const int Dp = padded_dim(D);
+    if (Dp != 4 && Dp != 6 && Dp != 10) return false;
+    int rc, lpp;
+    if (recon5_plan(MODE_REV_RECON_SYM, M, logd, &rc, &lpp) != 1) return false;
+    return rc * (Dp / 2) <= 6;
 }
 
 bool recon5_applies(int kind, int M, int N, int D, int logd, bool s1) {

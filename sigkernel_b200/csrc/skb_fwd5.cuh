@@ -181,7 +181,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     constexpr int F = 1 << LOGD;
     constexpr int R = RC * F;
     constexpr bool STORE = MODE == MODE_FWD_STORE, REVG = MODE == MODE_REV_GRAD;
-    constexpr bool EMIT = MODE == MODE_FWD_EMIT, RECON = MODE == MODE_REV_RECON;
+    // MODE_REV_RECON_SYM: the reversed sweep of Gram(X, X) over the UNORDERED pairs a <= b -- besides d k / d X_a it
+    // contracts the same sensitivities with the rows of X_a per node COLUMN (the partial sums travel down the lane chain
+    // with the exchange) and so also yields d k / d X_b: one sweep per unordered pair instead of two
+    constexpr bool RSYM = MODE == MODE_REV_RECON_SYM;
+    constexpr bool EMIT = MODE == MODE_FWD_EMIT, RECON = MODE == MODE_REV_RECON || RSYM;
     constexpr bool REVX = REVG || RECON;          // reversed sweep: sensitivities, gradient epilogue
     static_assert(MODE == 0 || STORE || REVG || EMIT || RECON, "unknown mode");
     static_assert(!(STORE || REVG) || (NW == 1 && LOGD >= 1), "the stored-grid modes use one warp per pair and 16-byte grid rows");
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // lane is through -- the epilogue runs once per pair and warp instead of once per pair and LANE (the lanes are
     // skewed, so every per-lane event costs the warp a full pass with one lane active)
     constexpr bool UFLUSH = RECON && GREG;
+    static_assert(!RSYM || (UFLUSH && NW == 1 && LPP == 32 && UNR == 3), "the unordered-pair sweep: one warp per pair, register accumulators");
     constexpr int Dp = 2 * DP2;
     constexpr bool XREG = (RC * DP2 <= ((LPP == 16 && R > 8) ? 12 : 8));   // x rows of the pair in registers (the 16-row
                                                                            // strips run 8 warps per SM: room for 12 double2)
@@ -245,6 +250,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // (this and the previous column) going down one lane
     __shared__ double2 txr[RECON ? 3 : 1][RECON ? H : 1][RECON ? NL + 1 : 1];
     __shared__ double2 sxr[RECON ? 3 : 1][RECON ? NL + 1 : 1];
+    // REV_RECON_SYM: partial column sums (sum of W, sum of W x_k over the node rows above and including a lane's) going down
+    __shared__ double2 syr[RSYM ? 3 : 1][RSYM ? DP2 : 1][RSYM ? NL + 1 : 1];
     if (KIND == KIND_RBF) {
         for (int j = glane; j < ETAB; j += 32 * NW) {
             const double e = p.kscale * __ldg(p.exp_tab + j * (2048 / ETAB));
@@ -304,6 +311,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     const unsigned txrb0 = RECON ? (unsigned)__cvta_generic_to_shared(&txr[0][0][RECON ? slot : 0]) : 0u;
     const unsigned sxrb0 = RECON ? (unsigned)__cvta_generic_to_shared(&sxr[0][RECON ? slot : 0]) : 0u;
     constexpr int SXQ = (NL + 1) * 16;                      // byte stride of sxr[q][slot]
+    const unsigned syrb0 = RSYM ? (unsigned)__cvta_generic_to_shared(&syr[0][0][RSYM ? slot : 0]) : 0u;
+    constexpr int SYQ = DP2 * (NL + 1) * 16;                // byte stride of syr[q][.][slot]
 
     double2 xr[XREG ? RC : 1][DP2];
     // !XREG: the lane's rows are staged in shared memory once per pair ([piece][lane]: conflict-free 16-byte
@@ -384,6 +393,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     // mod (fbuf_mask + 1) -- as many buffers as pairs fit between a lane's event and the flush of its warp (host: N (mask + 1) >= 34)
     constexpr int FBUF = (RC * Dp + R) * GL;      // doubles per buffer
     double* const gst = UFLUSH ? bstg + (size_t)(R + 2) * GL : nullptr;
+    // REV_RECON_SYM: the completed column sums of the pair the last lane is in, [node column][Dp], behind the parked sums
+    double* const ycol = RSYM ? gst + (size_t)(p.fbuf_mask + 1) * FBUF : nullptr;
     auto pair_boundaries = [&](int job_) {
         // slot of the pair in the forward launch's boundary arrays; under bsym the pair (a, b), a > b, reads the
         // transposed grid of (b, a)
@@ -729,6 +740,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             if (QT::ct) lds_f64x2<((Q + 2) % 3) * SXQ>(sxrb0, up_c, up_c1);
             else lds_f64x2<0>(sxrb0 + (unsigned)((qr == 0 ? 2 : qr - 1) * SXQ), up_c, up_c1);
         }
+        double ycs[RSYM ? Dp : 1];                // REV_RECON_SYM: column sums over the node rows above this lane's (column c)
+        if (RSYM) {
+#pragma unroll
+            for (int i = 0; i < (RSYM ? DP2 : 0); ++i) {
+                double vx, vy;
+                if (i == 0) lds_f64x2<((Q + 2) % 3) * SYQ>(syrb0, vx, vy);
+                if (i == 1) lds_f64x2<((Q + 2) % 3) * SYQ + TXH>(syrb0, vx, vy);
+                if (i == 2) lds_f64x2<((Q + 2) % 3) * SYQ + 2 * TXH>(syrb0, vx, vy);
+                if (i == 3) lds_f64x2<((Q + 2) % 3) * SYQ + 3 * TXH>(syrb0, vx, vy);
+                if (i == 4) lds_f64x2<((Q + 2) % 3) * SYQ + 4 * TXH>(syrb0, vx, vy);
+                ycs[RSYM ? 2 * i : 0] = pl == 0 ? 0.0 : vx;
+                ycs[RSYM ? 2 * i + 1 : 0] = pl == 0 ? 0.0 : vy;
+            }
+        }
         {
             double vx, vy;
             lds_f64x2<Q * TXQ>(txb, vx, vy);
@@ -764,6 +789,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 const double uc1 = rc > 0 ? Sprev[rc > 0 ? rc - 1 : 0] : up_c1;
                 const double T = (Scur[rc] - uc) - (Sprev[rc] - uc1);
                 const double W = KIND == KIND_RBF ? T * kc[rc] : T;
+                if (RSYM) {
+                    // the same W against this lane's rows of X_a (the STENCIL stream's pair: straight from L1, the register
+                    // copy belongs to the production stream): column sums for d k / d X_b at node column c
+                    const double* xs = reinterpret_cast<const double*>(xrow0[rc] + sxo);
+#pragma unroll
+                    for (int i = 0; i < DP2; ++i) {
+                        const double2 xv = ldg2(xs + 2 * i);
+                        ycs[RSYM ? 2 * i : 0] = fma(W, i == 0 ? 1.0 : xv.x, ycs[RSYM ? 2 * i : 0]);
+                        ycs[RSYM ? 2 * i + 1 : 0] = fma(W, xv.y, ycs[RSYM ? 2 * i + 1 : 0]);
+                    }
+                }
                 if (GREG) {
                     // the prepared y row is (norm term, y_1 .. y_D, 0 ...): slot 0 accumulates W itself
 #pragma unroll
@@ -783,6 +819,23 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             Slast_prev = Slast_cur;
             Slast_cur = Scur[RC - 1];
             if (RECON) sts_f64x2<Q * SXQ + 16>(sxrb, Slast_cur, Slast_prev);
+            if (RSYM) {
+                // the same W, contracted with this lane's rows of X_a: column sums for d k / d X_b at node column c
+                const unsigned syrb = syrb0 + (unsigned)(qr * SYQ);
+#pragma unroll
+                for (int i = 0; i < DP2; ++i) {
+                    if (i == 0) sts_f64x2<Q * SYQ + 16>(syrb, ycs[0], ycs[RSYM ? 1 : 0]);
+                    if (i == 1) sts_f64x2<Q * SYQ + TXH + 16>(syrb, ycs[RSYM ? 2 : 0], ycs[RSYM ? 3 : 0]);
+                    if (i == 2) sts_f64x2<Q * SYQ + 2 * TXH + 16>(syrb, ycs[RSYM && Dp > 4 ? 4 : 0], ycs[RSYM && Dp > 4 ? 5 : 0]);
+                    if (i == 3) sts_f64x2<Q * SYQ + 3 * TXH + 16>(syrb, ycs[RSYM && Dp > 6 ? 6 : 0], ycs[RSYM && Dp > 6 ? 7 : 0]);
+                    if (i == 4) sts_f64x2<Q * SYQ + 4 * TXH + 16>(syrb, ycs[RSYM && Dp > 8 ? 8 : 0], ycs[RSYM && Dp > 8 ? 9 : 0]);
+                }
+                if (pl == LPP - 1 && c < N) {
+                    double2* yc = reinterpret_cast<double2*>(ycol + (size_t)c * Dp);
+#pragma unroll
+                    for (int i = 0; i < DP2; ++i) yc[i] = make_double2(ycs[RSYM ? 2 * i : 0], ycs[RSYM ? 2 * i + 1 : 0]);
+                }
+            }
             syp += Dp;
         }
 
@@ -882,6 +935,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                             ga[GREG ? rc : 0][GREG ? 2 * i : 0] = 0.0;
                             ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = 0.0;
                         }
+                    if (RSYM) sxo = xo;
                     syo = yo;
                     syp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + syo);
                 }
@@ -1008,7 +1062,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (ent.x >= 0) {
                     const long pi = p.job0 + ent.x;                      // GRAM: a * B + b; BATCH: a
                     const int a = ent.w;
-                    const int b = p.pairs == PAIRS_BATCH ? a : (int)(pi - (long)a * p.B);
+                    // (SYM: the pairs a <= b row by row, pi = a A - a (a - 1) / 2 + (b - a))
+                    const int b = p.pairs == PAIRS_BATCH ? a
+                                  : (RSYM ? a + (int)(pi - ((long)a * p.A - (long)a * (a - 1) / 2)) : (int)(pi - (long)a * p.B));
                     // fused loss head: d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
                     const double coef = p.gradX == nullptr ? 0.0 : (p.gout ? __ldg(p.gout + pi) : (a == b ? p.w_diag : p.w_off));
                     double* gx = p.gradX ? p.gradX + (long)a * (M * D) : nullptr;
@@ -1060,6 +1116,26 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                     if (coef != 0.0) atomicAdd(gx + go + k, coef * gv);
                                 }
                         }
+                    }
+                    if (RSYM) {
+                        // d loss / d X_b += coef * d k(X_a, X_b) / d X_b from the column sums the last lane collected
+                        // (node columns are reversed like the rows: column q is point N - 1 - q of X_b)
+                        __syncwarp();
+                        if (coef != 0.0) {
+                            double* gxb = p.gradX + (long)b * (M * D);
+                            const double* syb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + (unsigned)ent.z);
+                            for (int q = lane; q < N; q += 32) {
+                                const double* part = ycol + (size_t)q * Dp;
+                                const double* yrw = syb + q * Dp;
+                                const double sW = part[0];
+                                for (int k = 0; k < D; ++k) {
+                                    const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(-p.gscale * __ldg(yrw + 1 + k), sW, part[1 + k])
+                                                                       : p.inv_kscale * part[1 + k];
+                                    atomicAdd(gxb + (N - 1 - q) * D + k, coef * gv);
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
             }

@@ -88,6 +88,7 @@ int solver_rows_per_lane(int M, int logd);
 // generic fallback: coarse increments (pairs, M-1, N-1) from a static matrix; static matrix of the fused kinds
 int launch_coarse_increments(const double* Ks, double* incc, long pairs, int M, int N, double scale4, bool exact, cudaStream_t st);
 int launch_static_matrix(const KArgs& a, int kind, long job0, long njobs, double* Ks, cudaStream_t st);
+bool recon5_sym_applies(int kind, int M, int N, int D, int logd, bool s1);   // MODE_REV_RECON_SYM instantiated for the shape
 void set_deriv_mode(int mode);                                   // skb_deriv.cu: 0 = bit-exact diagonal kernel always
 int launch_rank_barrier(const KArgs& a, cudaStream_t st);      // the in-kernel rank barrier on its own (a rank without pairs)
 // backward on materialised grids (skb_generic_adj.cu)

@@ -16,8 +16,9 @@ template <int KIND, int RC, int LOGD, int DP2, int MODE, int LPP, int NW>
 int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     constexpr int R = RC << LOGD;
     // resident blocks per SM the register budget is sized for (the reversed sweep carries two solutions)
-    constexpr int MINB = MODE == MODE_REV_RECON ? (NW > 1 ? (NW == 2 ? 4 : 2) : (R <= 4 ? 12 : 8))
-                                                : (NW > 1 ? (NW == 2 ? 8 : 4) : (R <= 4 ? 16 : 12));
+    constexpr int MINB = MODE == MODE_REV_RECON_SYM ? 8
+                         : MODE == MODE_REV_RECON ? (NW > 1 ? (NW == 2 ? 4 : 2) : (R <= 4 ? 12 : 8))
+                                                  : (NW > 1 ? (NW == 2 ? 8 : 4) : (R <= 4 ? 16 : 12));
     // the reversed sweep with 16 lanes per pair is too much code to unroll 3x (110 KB: it stalled on instruction fetch)
     constexpr int UNR = (MODE == MODE_REV_RECON && LPP == 16) ? 1 : 3;
     int wpsm = get_warps_per_sm() > 0 ? get_warps_per_sm() / NW : MINB;
@@ -27,10 +28,11 @@ int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     const long need = LPP == 16 ? ((long)a.njobs + 1) / 2 : (long)a.njobs;      // two pair streams per warp at 16 lanes per pair
     if (nb > need) nb = need;
     size_t smem = 0;
-    if (MODE == MODE_REV_RECON) {
+    if (MODE == MODE_REV_RECON || MODE == MODE_REV_RECON_SYM) {
         constexpr bool GREG = RC * DP2 <= 6;
         smem = ((GREG ? 0 : (size_t)RC * (a.D + 1)) + (size_t)(R + 2)) * 32 * NW * sizeof(double);
         if (GREG) smem += (size_t)(a.fbuf_mask + 1) * (RC * 2 * DP2 + R) * 32 * NW * sizeof(double);   // parked sums + first columns
+        if (MODE == MODE_REV_RECON_SYM) smem += (size_t)a.N * 2 * DP2 * sizeof(double);                // column sums of one pair
     }
     auto kern = fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR, MODE, LPP>;
     if (smem > 8 * 1024) {
@@ -42,8 +44,22 @@ int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     return check_launch();
 }
 
+template <int KIND, int RC, int LOGD, int DP2, int LPP, int NW>
+int launch_recon5_sym(const KArgs& a, cudaStream_t st) {
+    if constexpr (LPP == 32 && NW == 1 && RC * DP2 <= 6) return launch_recon5_one<KIND, RC, LOGD, DP2, MODE_REV_RECON_SYM, 32, 1>(a, st);
+    else return SKB_ERR_UNSUPPORTED;
+}
+
 template <int KIND, int RC, int LOGD, int LPP, int NW>
 int launch_recon5_shape(int mode, int dp2, const KArgs& a, cudaStream_t st) {
+    if (mode == MODE_REV_RECON_SYM) {
+        switch (dp2) {
+            case 2: return launch_recon5_sym<KIND, RC, LOGD, 2, LPP, NW>(a, st);
+            case 3: return launch_recon5_sym<KIND, RC, LOGD, 3, LPP, NW>(a, st);
+            case 5: return launch_recon5_sym<KIND, RC, LOGD, 5, LPP, NW>(a, st);
+            default: return SKB_ERR_UNSUPPORTED;
+        }
+    }
     if (mode == MODE_FWD_EMIT) {
         switch (dp2) {
             case 2: return launch_recon5_one<KIND, RC, LOGD, 2, MODE_FWD_EMIT, LPP, NW>(a, st);

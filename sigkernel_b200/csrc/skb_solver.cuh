@@ -43,7 +43,8 @@
 
 namespace skb {
 
-constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5;
+constexpr int MODE_FWD = 0, MODE_FWD_STORE = 1, MODE_REV_S = 2, MODE_REV_GRAD = 3, MODE_REV_RECON = 4, MODE_FWD_EMIT = 5,
+              MODE_REV_RECON_SYM = 6;
 
 // exp(x) for the RBF static kernel: x <= ~0 (|x - y|^2 >= 0 up to rounding), possibly hugely negative.
 // Table-driven: x = (256 n + j) ln2/256 + r, exp(x) = 2^n * T[j] * e^r with T[j] = 2^(j/256) in shared

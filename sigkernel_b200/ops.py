@@ -198,6 +198,12 @@ def adjoint_plan(M, N, D, dyadic_order, static_kind, naive=False):
                                 _lib.SCHEME_S1 if naive else _lib.SCHEME_S2)
 
 
+def adjoint_sym_supported(M, D, dyadic_order, static_kind, naive=False):
+    """True if the backward of Gram(X, X) can run one reversed sweep per UNORDERED pair (sigkernel_backward_vjp, pairs 'sym')."""
+    return bool(lib.skb_adjoint_sym_supported(int(M), int(D), int(dyadic_order), _STATIC[static_kind],
+                                              _lib.SCHEME_S1 if naive else _lib.SCHEME_S2))
+
+
 def sigkernel_forward_ctx(X, Y, static_kind, static_param, dyadic_order, pairs="gram", naive=False):
     """Forward values plus the boundary context the lazy backward needs (last row / column of every pair's grid).
     Returns (k, ctx) or None when the shape is outside the reconstruction kernels (use sigkernel_forward_backward)."""
@@ -224,7 +230,9 @@ def sigkernel_forward_ctx(X, Y, static_kind, static_param, dyadic_order, pairs="
 def sigkernel_backward_vjp(X, Y, static_kind, static_param, dyadic_order, pairs, ctx, ctx_pairs, grad_out=None,
                            w_diag=0.0, w_off=0.0, out_scale=1.0, out_scale_dev=None, into=None, want_points=False,
                            naive=False):
-    """Reversed sweep over every ordered pair of `pairs` ('gram' / 'batch') contracted with d loss / d K on the fly:
+    """pairs 'sym' (Y is X, ctx_pairs 'sym', w_diag / w_off only): one sweep per unordered pair, gradient w.r.t. both
+    arguments -- gradX = sum over ordered pairs (a,b) of coef(a,b) d k(X_a,X_b)/d X.  Otherwise:
+    Reversed sweep over every ordered pair of `pairs` ('gram' / 'batch') contracted with d loss / d K on the fly:
     gradX (A,M,D) fp64 = [into +] out_scale * [out_scale_dev] * sum_b coef(a,b) d k(X_a,Y_b)/d X_a, coef = grad_out[a,b]
     or (w_diag on a == b, w_off elsewhere).  `ctx` comes from sigkernel_forward_ctx(..., ctx_pairs).  The (A,B,M,D)
     tensor of the reference (sigkernel.py:405-416) is only materialised when want_points."""

@@ -237,7 +237,10 @@ class _SigLoss(torch.autograd.Function):
             P, Q = T[first], T[second]
             if need_grad and gscale is not None:
                 if pairs == "sym":
-                    pairs = "gram"        # with gradients the full square is solved (see _SigKernelGram.forward)
+                    if ops.adjoint_sym_supported(P.shape[1], P.shape[2], dyadic_order, kind, _naive_solver):
+                        gscale = 1.0      # one reversed sweep per unordered pair yields both halves of the gradient
+                    else:
+                        pairs = "gram"    # else the full square is solved (see _SigKernelGram.forward)
                 G, bctx = ops.sigkernel_forward_ctx(P, Q, kind, param, dyadic_order, pairs, _naive_solver)
                 plan.append((second, pairs, w_diag, w_off, gscale, len(saved)))
                 saved.append(bctx)
@@ -261,7 +264,7 @@ class _SigLoss(torch.autograd.Function):
         grad = None
         for second, pairs, w_diag, w_off, gscale, k in ctx.plan:
             Q = X if second == "X" else Y
-            grad = ops.sigkernel_backward_vjp(X, Q, kind, param, d, "batch" if pairs == "batch" else "gram", saved[k], pairs,
+            grad = ops.sigkernel_backward_vjp(X, Q, kind, param, d, pairs, saved[k], pairs,
                                               w_diag=w_diag, w_off=w_off, out_scale=gscale, out_scale_dev=grad_output,
                                               into=grad, naive=naive)
         return (grad if ctx.in_dtype == torch.float64 else grad.to(ctx.in_dtype)), None, None, None, None, None

@@ -250,6 +250,47 @@ def test_backward_of_any_length_vs_analytic_oracle(skb, O, A, B, M, N, D, d, nai
     assert grad_err(Xg.grad.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
 
 
+@pytest.mark.parametrize("A,M,D,d,static", [(9, 20, 3, 1, "rbf"), (6, 64, 3, 1, "rbf"), (5, 33, 5, 2, "rbf"), (4, 60, 2, 0, "linear"),
+                                            (7, 12, 2, 3, "rbf"), (3, 64, 2, 0, "rbf"), (4, 30, 8, 1, "linear")])
+def test_unordered_pair_sweep_matches_the_full_square(skb, O, A, M, D, d, static):
+    """Gram(X, X) in a loss head: one reversed sweep per unordered pair (d k / d X_a and d k / d X_b from the same
+    sensitivities) against the two-sweeps-per-pair path (adjoint mode 3) and against the oracle's analytic gradient."""
+    X = make_paths("bm", 900 + M, (A, M, D))
+    par = 0.8 if static == "rbf" else 1.0
+    assert skb.ops.adjoint_sym_supported(M, D, d, static)
+    assert not skb.ops.adjoint_sym_supported(100, 2, 0, static)      # strips whose sums do not fit registers: two sweeps per pair
+    # (loss heads weigh the diagonal of Gram(X, X) with zero; the diagonal pairs k(X_a, X_a) are the fastest-growing grids, where the
+    #  reconstruction is accurate to ~1e-8 rather than 1e-12: checked separately below with the tolerance that goes with it)
+    w_diag, w_off = 0.0, -0.7
+    Xc = X.cuda()
+    res = skb.ops.sigkernel_forward_ctx(Xc, Xc, static, par, d, "sym")
+    assert res is not None
+    G, bctx = res
+    g_sym = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", w_diag=w_diag, w_off=w_off)
+    # oracle: sum over ordered pairs of coef(a,b) k(X_a, X_b), gradient w.r.t. both arguments = 2 * sum_b coef d1 k (coef symmetric)
+    ok = O.RBFKernel(par) if static == "rbf" else O.LinearKernel()
+    _, gp_ref, _ = O.gram_grad_points_analytic(X, X, ok, d)
+    coef = torch.full((A, A), w_off, dtype=torch.float64) + (w_diag - w_off) * torch.eye(A, dtype=torch.float64)
+    expect = 2.0 * torch.einsum('ab,abmd->amd', coef, gp_ref)
+    assert grad_err(g_sym.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
+    g_diag = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", w_diag=1.0, w_off=0.0)
+    expect = 2.0 * torch.einsum('aamd->amd', gp_ref)
+    assert grad_err(g_diag.cpu().numpy(), expect.numpy()) <= 1e-6
+    # and the public loss head with the sweep switched off (mode 3) gives the same gradient
+    Y = make_paths("bm", 901 + M, (A + 1, M, D)).cuda()
+    sk = skb.SigKernel(skb.RBFKernel(par) if static == "rbf" else skb.LinearKernel(), d)
+    grads = []
+    for mode in (-1, 3):
+        skb._lib.lib.skb_set_adjoint_mode(mode)
+        try:
+            Xg = Xc.clone().requires_grad_(True)
+            sk.compute_mmd(Xg, Y).backward()
+            grads.append(Xg.grad.clone())
+        finally:
+            skb._lib.lib.skb_set_adjoint_mode(-1)
+    assert grad_err(grads[0].cpu().numpy(), grads[1].cpu().numpy()) <= 1e-9
+
+
 def test_reconstruction_agrees_with_the_stored_grid_kernels(skb):
     X, Y = make_paths("rand", 81, (6, 40, 3)).cuda(), make_paths("rand", 82, (5, 33, 3)).cuda()
     lib = skb._lib.lib
