@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     __shared__ double2 sxr[RECON ? 3 : 1][RECON ? NL + 1 : 1];
     // REV_RECON_SYM: partial column sums (sum of W, sum of W x_k over the node rows above and including a lane's) going down
     __shared__ double2 syr[RSYM ? 3 : 1][RSYM ? DP2 : 1][RSYM ? NL + 1 : 1];
+    // REV_RECON_SYM: the lane's rows of the STENCIL stream's X_a (copied from the production stream's registers when the
+    // stencil stream moves on to that pair; re-reading them from global every step stalled on L2: long_scoreboard 1.3 per issue)
+    __shared__ double2 xss[RSYM ? RC * DP2 : 1][RSYM ? 32 * NW : 1];
     if (KIND == KIND_RBF) {
         for (int j = glane; j < ETAB; j += 32 * NW) {
             const double e = p.kscale * __ldg(p.exp_tab + j * (2048 / ETAB));
@@ -282,6 +285,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (RECON) {
                     for (int h = 0; h < H; ++h) txr[RECON ? q : 0][RECON ? h : 0][RECON ? slot : 0] = make_double2(1.0, 1.0);
                     sxr[RECON ? q : 0][RECON ? slot : 0] = make_double2(0.0, 0.0);
+                }
+                if (RSYM) {
+                    for (int i = 0; i < DP2; ++i) syr[RSYM ? q : 0][RSYM ? i : 0][RSYM ? slot : 0] = make_double2(0.0, 0.0);
                 }
             }
             ring_s[sid][0] = make_int4(has_job ? first_job : -1, (int)xo, (int)yo, pa);
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     double* const gst = UFLUSH ? bstg + (size_t)(R + 2) * GL : nullptr;
     // REV_RECON_SYM: the completed column sums of the pair the last lane is in, [node column][Dp], behind the parked sums
     double* const ycol = RSYM ? gst + (size_t)(p.fbuf_mask + 1) * FBUF : nullptr;
+    const unsigned ycol_s = RSYM ? (unsigned)__cvta_generic_to_shared(ycol) : 0u;
     auto pair_boundaries = [&](int job_) {
         // slot of the pair in the forward launch's boundary arrays; under bsym the pair (a, b), a > b, reads the
         // transposed grid of (b, a)
@@ -750,8 +757,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 if (i == 2) lds_f64x2<((Q + 2) % 3) * SYQ + 2 * TXH>(syrb0, vx, vy);
                 if (i == 3) lds_f64x2<((Q + 2) % 3) * SYQ + 3 * TXH>(syrb0, vx, vy);
                 if (i == 4) lds_f64x2<((Q + 2) % 3) * SYQ + 4 * TXH>(syrb0, vx, vy);
-                ycs[RSYM ? 2 * i : 0] = pl == 0 ? 0.0 : vx;
-                ycs[RSYM ? 2 * i + 1 : 0] = pl == 0 ? 0.0 : vy;
+                ycs[RSYM ? 2 * i : 0] = vx;        // (slot 0, what lane 0 reads, is zero for good)
+                ycs[RSYM ? 2 * i + 1 : 0] = vy;
             }
         }
         {
@@ -790,12 +797,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 const double T = (Scur[rc] - uc) - (Sprev[rc] - uc1);
                 const double W = KIND == KIND_RBF ? T * kc[rc] : T;
                 if (RSYM) {
-                    // the same W against this lane's rows of X_a (the STENCIL stream's pair: straight from L1, the register
-                    // copy belongs to the production stream): column sums for d k / d X_b at node column c
-                    const double* xs = reinterpret_cast<const double*>(xrow0[rc] + sxo);
+                    // the same W against this lane's rows of X_a (the STENCIL stream's pair: the register copy belongs to the
+                    // production stream): column sums for d k / d X_b at node column c
 #pragma unroll
                     for (int i = 0; i < DP2; ++i) {
-                        const double2 xv = ldg2(xs + 2 * i);
+                        const double2 xv = xss[RSYM ? rc * DP2 + i : 0][RSYM ? glane : 0];
                         ycs[RSYM ? 2 * i : 0] = fma(W, i == 0 ? 1.0 : xv.x, ycs[RSYM ? 2 * i : 0]);
                         ycs[RSYM ? 2 * i + 1 : 0] = fma(W, xv.y, ycs[RSYM ? 2 * i + 1 : 0]);
                     }
@@ -830,10 +836,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     if (i == 3) sts_f64x2<Q * SYQ + 3 * TXH + 16>(syrb, ycs[RSYM && Dp > 6 ? 6 : 0], ycs[RSYM && Dp > 6 ? 7 : 0]);
                     if (i == 4) sts_f64x2<Q * SYQ + 4 * TXH + 16>(syrb, ycs[RSYM && Dp > 8 ? 8 : 0], ycs[RSYM && Dp > 8 ? 9 : 0]);
                 }
-                if (pl == LPP - 1 && c < N) {
-                    double2* yc = reinterpret_cast<double2*>(ycol + (size_t)c * Dp);
+                if (pl == LPP - 1) {
+                    const unsigned yc = ycol_s + (unsigned)(c * (Dp * 8));
 #pragma unroll
-                    for (int i = 0; i < DP2; ++i) yc[i] = make_double2(ycs[RSYM ? 2 * i : 0], ycs[RSYM ? 2 * i + 1 : 0]);
+                    for (int i = 0; i < DP2; ++i)
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(yc + 16 * i), "d"(ycs[RSYM ? 2 * i : 0]), "d"(ycs[RSYM ? 2 * i + 1 : 0]) : "memory");
                 }
             }
             syp += Dp;
@@ -935,7 +942,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                             ga[GREG ? rc : 0][GREG ? 2 * i : 0] = 0.0;
                             ga[GREG ? rc : 0][GREG ? 2 * i + 1 : 0] = 0.0;
                         }
-                    if (RSYM) sxo = xo;
+                    if (RSYM) {
+                        // the production stream's rows are those of the pair the stencil stream starts now
+#pragma unroll
+                        for (int rc = 0; rc < RC; ++rc)
+#pragma unroll
+                            for (int i = 0; i < DP2; ++i) xss[RSYM ? rc * DP2 + i : 0][RSYM ? glane : 0] = xr[XREG ? rc : 0][XREG ? i : 0];
+                    }
                     syo = yo;
                     syp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + syo);
                 }

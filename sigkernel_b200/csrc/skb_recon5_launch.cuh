@@ -16,7 +16,7 @@ template <int KIND, int RC, int LOGD, int DP2, int MODE, int LPP, int NW>
 int launch_recon5_one(const KArgs& a, cudaStream_t st) {
     constexpr int R = RC << LOGD;
     // resident blocks per SM the register budget is sized for (the reversed sweep carries two solutions)
-    constexpr int MINB = MODE == MODE_REV_RECON_SYM ? 8
+    constexpr int MINB = MODE == MODE_REV_RECON_SYM ? (R <= 4 ? 12 : 8)
                          : MODE == MODE_REV_RECON ? (NW > 1 ? (NW == 2 ? 4 : 2) : (R <= 4 ? 12 : 8))
                                                   : (NW > 1 ? (NW == 2 ? 8 : 4) : (R <= 4 ? 16 : 12));
     // the reversed sweep with 16 lanes per pair is too much code to unroll 3x (110 KB: it stalled on instruction fetch)

@@ -86,8 +86,12 @@ __device__ __forceinline__ void job_decode(const KArgs& p, long j, int& a, int& 
     } else if (p.pairs == PAIRS_BATCH) {
         a = b = (int)j;
     } else {  // upper triangle, row-major: row a holds (a,a) .. (a,A-1)
-        int r = 0;
-        long off = 0;
+        // off(r) = r (2A - r + 1) / 2 <= j < off(r + 1): closed form, then at most a step of correction either way
+        const double t = 2.0 * p.A + 1.0;
+        int r = (int)((t - sqrt(fmax(t * t - 8.0 * (double)j, 0.0))) * 0.5);
+        r = r < 0 ? 0 : (r > p.A - 1 ? p.A - 1 : r);
+        long off = (long)r * (2L * p.A - r + 1) / 2;
+        while (off > j) { --r; off = (long)r * (2L * p.A - r + 1) / 2; }
         while (off + (p.A - r) <= j) { off += p.A - r; ++r; }
         a = r;
         b = r + (int)(j - off);
