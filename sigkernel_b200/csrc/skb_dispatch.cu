@@ -246,11 +246,12 @@ bool fwd5_scaled_exp(int M, int logd, int D) {
 }
 
 bool fwd5_applies(int kind, int M, int N, int D, int logd, bool s1) {
-    if (s1 || N < 4) return false;
+    if (N < 4) return false;
     if (kind != KIND_RBF && kind != KIND_LINEAR) return false;
     const int Dp = padded_dim(D);
     if (Dp != 4 && Dp != 6 && Dp != 10) return false;
-    return fwd5_plan(M, logd, nullptr) > 0;
+    const int nw = fwd5_plan(M, logd, nullptr);
+    return s1 ? nw == 1 : nw > 0;           // scheme S1 is instantiated for the single-warp variants
 }
 
 // 2^(j/2048), j = 0..2047, in device memory: every block of the RBF kernels copies (a stride of) it, times kscale, into

@@ -173,8 +173,9 @@ template <> struct step_q<int> {
     static __device__ __forceinline__ int runtime(int q) { return q; }
 };
 
-template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0, int LPP = 32>
+template <int KIND, int RC, int LOGD, int DP2, int NW, int MINB, int UNR, int MODE = 0, int LPP = 32, bool S1 = false>
 __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
+    static_assert(!S1 || (MODE == 0 && NW == 1), "scheme S1 (_naive_solver): single-warp forward variants only");
     static_assert(LPP == 32 || (LPP == 16 && NW == 1 && (MODE == 0 || MODE == MODE_FWD_EMIT || MODE == MODE_REV_RECON)),
                   "16 lanes per pair: one warp; forward, forward + boundaries, reconstruction adjoint");
     constexpr int NSTR = 32 / LPP;               // pair streams per warp
@@ -597,8 +598,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
             const double dlo = REVX ? dB[rc] - dA[rc] : dA[rc];
             const double dhi = rc + 1 < RC ? (REVX ? dB[rc + 1 < RC ? rc + 1 : rc] - dA[rc + 1 < RC ? rc + 1 : rc] : dA[rc + 1 < RC ? rc + 1 : rc]) : dn;
             const double el = dhi - dlo;
-            cb[rc] = fma(el, el, -1.0);
-            ca[rc] = fma(el, p.sqrt3, cb[rc] + 2.0);
+            if (S1) {
+                // _naive_solver (cython_backend.pyx:27): a = 1 + g/2, b = 1
+                cb[rc] = -1.0;
+                ca[rc] = fma(el, p.sqrt3, 1.0);
+            } else {
+                cb[rc] = fma(el, el, -1.0);
+                ca[rc] = fma(el, p.sqrt3, cb[rc] + 2.0);
+            }
         }
         // REV_RECON: coefficients of the backward update u00 = (a/b)(u10 + u01) - (1/b) u11:  cib = -1/b = 1/cb, cia = -ca cib
         double cia[RECON ? RC : 1], cib[RECON ? RC : 1];

@@ -11,7 +11,8 @@ static int launch_l16(const KArgs& a, cudaStream_t st) {
     long nb = (long)sm_count() * wpsm;
     const long need = ((long)a.njobs + 1) / 2;                   // two pair streams per warp
     if (nb > need) nb = need;
-    fwd5_kernel<KIND, RC, LOGD, DP2, 1, MINB, UNR, 0, 16><<<(unsigned)nb, 32, 0, st>>>(a);
+    if (a.s1) fwd5_kernel<KIND, RC, LOGD, DP2, 1, MINB, UNR, 0, 16, true><<<(unsigned)nb, 32, 0, st>>>(a);
+    else fwd5_kernel<KIND, RC, LOGD, DP2, 1, MINB, UNR, 0, 16><<<(unsigned)nb, 32, 0, st>>>(a);
     return check_launch();
 }
 

@@ -11,7 +11,8 @@ static int launch_fwd5(const KArgs& a, cudaStream_t st) {
     if (bpsm < 1) bpsm = 1;
     long nb = (long)sm_count() * bpsm;
     if (nb > a.njobs) nb = a.njobs;
-    fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR><<<(unsigned)nb, 32 * NW, 0, st>>>(a);
+    if (NW == 1 && a.s1) fwd5_kernel<KIND, RC, LOGD, DP2, 1, MINB * NW, UNR, 0, 32, true><<<(unsigned)nb, 32, 0, st>>>(a);
+    else fwd5_kernel<KIND, RC, LOGD, DP2, NW, MINB, UNR><<<(unsigned)nb, 32 * NW, 0, st>>>(a);
     return check_launch();
 }
 

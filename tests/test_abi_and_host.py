@@ -187,7 +187,8 @@ def test_dispatch_plans_for_the_baseline_configs():
     assert lib.skb_forward_plan(100, 11, 8, 1, RBF, S2) == 6     # len_x > 64: 32 lanes per pair, 2 warps
     assert lib.skb_forward_plan(128, 128, 8, 2, RBF, S2) == 5    # cfg5: one warp per pair, 16-row strips
     assert lib.skb_forward_plan(250, 9, 3, 2, RBF, S2) == 7      # four warps per pair
-    assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S1) == 1      # _naive_solver: v4 kernel
+    assert lib.skb_forward_plan(64, 64, 5, 2, RBF, S1) == 4      # _naive_solver: an S1 instantiation of the single-warp fwd5 variants
+    assert lib.skb_forward_plan(250, 9, 3, 2, RBF, S1) == 1      # ... several warps per pair: v4 kernel
     assert lib.skb_forward_plan(64, 3, 5, 2, RBF, S2) == 1       # len_y < 4: v4 kernel
     assert lib.skb_forward_plan(64, 64, 12, 2, RBF, S2) == 1     # dim + 1 > 10: generic-width v4 kernel
     assert lib.skb_forward_plan(1000, 6, 2, 0, RBF, S2) == 0     # beyond the register-resident kernels: row bands
