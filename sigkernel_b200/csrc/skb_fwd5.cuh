@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         for (int d0 = 0; d0 < DEPTH; ++d0) stage_issue(d0, -1, 0);     // the first DEPTH steps are virtual for every lane
     }
 
+    double* ebr = p.brow;                         // FWD_EMIT: where this step's part of the pair's last row goes
     double u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = 1.0;
@@ -722,16 +723,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
         }
         if (EMIT) {
             // the lane that owns grid row MM-1 leaves u[MM, c F + 1 ..] (the last row of the grid) behind
+            // (ebr walks along the pair's row, F values per step; it is re-aimed when the stencil stream moves on to a pair, and
+            //  u[MM, 0] = 1 is written with the last column)
             if ((unsigned)orc < (unsigned)RC && real_col) {
-                double* br = p.brow + (p.job0 + sjob) * p.brow_stride + 1 + (long)c * F;
 #pragma unroll
                 for (int rc = 0; rc < RC; ++rc)
                     if (rc == orc) {
 #pragma unroll
-                        for (int f = 0; f < F; ++f) br[f] = U[(rc + 1) * F - 1][f];
+                        for (int f = 0; f < F; ++f) ebr[f] = U[(rc + 1) * F - 1][f];
                     }
-                if (c == 0) br[-1] = 1.0;
             }
+            ebr += F;
         }
         if (NW > 1) __syncthreads(); else __syncwarp();
         dn = lds_f64<Q * DXQ + 8>(dxb);
@@ -887,6 +889,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 for (int r = 0; r < R; ++r)
                     if ((long)pl * R + r < MMl) bc[r] = u[r];
                 if (pl == 0) bc[-1] = 1.0;
+                if ((unsigned)orc < (unsigned)RC) p.brow[(p.job0 + sjob) * p.brow_stride] = 1.0;
             }
             if (RECON && cc == N - 2 && pl == 0) {
                 cbr = nbr + (NNf - 1);
@@ -1031,6 +1034,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                 }
                 c = 0;
                 sjob = pjob;
+                if (EMIT) ebr = p.brow + (p.job0 + (pjob >= 0 ? pjob : 0)) * p.brow_stride + 1;
             }
             if (cc == pc) {
                 // the production column wraps: next pair
