@@ -925,6 +925,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         job_decode(p, p.job0 + sjob, a, b);
                         if (p.n_peer > 0) {
                             // both mirror entries of every rank's copy of G (peer memory)
+#pragma unroll 1
                             for (int q = 0; q < p.n_peer; ++q) {
                                 p.out_peer[q][(long)a * p.B + b] = res;
                                 p.out_peer[q][(long)b * p.B + a] = res;
@@ -935,6 +936,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         }
                     } else if (p.n_peer > 0) {
                         // one 8-byte store per rank: this pair's entry of every rank's copy of G (peer memory)
+#pragma unroll 1
                         for (int q = 0; q < p.n_peer; ++q) p.out_peer[q][p.job0 + sjob] = res;
                     } else {
                         p.out[p.job0 + sjob] = res;   // GRAM: job = a * B + b; BATCH: job = a

@@ -79,22 +79,29 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     return tiny ? 0.0 : res;
 }
 
+// upper triangle, row-major: row a holds (a,a) .. (a,A-1); off(r) = r (2A - r + 1) / 2 <= j < off(r + 1): closed form, then at
+// most a step of correction either way.  Kept out of line: the kernels decode a job in several places of their unrolled
+// loops, and the square root would be inlined into each of them (the symmetric enumeration is the rare case).
+static __device__ __noinline__ int2 sym_job_decode(int A, long j) {
+    const double t = 2.0 * A + 1.0;
+    int r = (int)((t - sqrt(fmax(t * t - 8.0 * (double)j, 0.0))) * 0.5);
+    r = r < 0 ? 0 : (r > A - 1 ? A - 1 : r);
+    long off = (long)r * (2L * A - r + 1) / 2;
+    while (off > j) { --r; off = (long)r * (2L * A - r + 1) / 2; }
+    while (off + (A - r) <= j) { off += A - r; ++r; }
+    return make_int2(r, r + (int)(j - off));
+}
+
 __device__ __forceinline__ void job_decode(const KArgs& p, long j, int& a, int& b) {
     if (p.pairs == PAIRS_GRAM) {
         a = (int)(j / p.B);
         b = (int)(j - (long)a * p.B);
     } else if (p.pairs == PAIRS_BATCH) {
         a = b = (int)j;
-    } else {  // upper triangle, row-major: row a holds (a,a) .. (a,A-1)
-        // off(r) = r (2A - r + 1) / 2 <= j < off(r + 1): closed form, then at most a step of correction either way
-        const double t = 2.0 * p.A + 1.0;
-        int r = (int)((t - sqrt(fmax(t * t - 8.0 * (double)j, 0.0))) * 0.5);
-        r = r < 0 ? 0 : (r > p.A - 1 ? p.A - 1 : r);
-        long off = (long)r * (2L * p.A - r + 1) / 2;
-        while (off > j) { --r; off = (long)r * (2L * p.A - r + 1) / 2; }
-        while (off + (p.A - r) <= j) { off += p.A - r; ++r; }
-        a = r;
-        b = r + (int)(j - off);
+    } else {
+        const int2 ab = sym_job_decode(p.A, j);
+        a = ab.x;
+        b = ab.y;
     }
 }
 
