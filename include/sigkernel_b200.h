@@ -257,13 +257,12 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
  *                         carries the reference's factor 2 for Gram(X, X) (sigkernel.py:410-412), out_scale_dev (device,
  *                         may be NULL) the upstream gradient of a scalar loss.  g is summed with fp64 atomics (the order
  *                         over b varies from run to run).  grad_points (pairs, M, D) is also written if not NULL; one of
- *                         gradX (A, M, D) and grad_points must be given.  pairs = SKB_PAIRS_SYM (Y = X, ctx_pairs = SYM, loss-head
- *                         weights only, gradX only; skb_adjoint_sym_supported): ONE sweep per unordered pair a <= b --
- *                         the same sensitivities are also contracted with the rows of X_a per node column, which gives
- *                         d k / d X_b (cython_backend.pyx:76-97 solves the triangle only in the forward; here the backward
- *                         does too) --
- *                             g[c] = sum over ORDERED pairs (a, b) of coef(a, b) d k(X_a, X_b) / d X_c   (both arguments),
- *                         half the sweeps of the GRAM call with out_scale 2 that it replaces.  Workspace: skb_bwd_vjp_workspace_bytes (smaller is accepted: without room for
+ *                         gradX (A, M, D) and grad_points must be given.  pairs = SKB_PAIRS_SYM (Y = X, ctx_pairs = SYM, gradX
+ *                         only; skb_adjoint_sym_supported): the SAME sum g[a] = sum_b coef(a, b) d k(X_a, X_b) / d X_a from ONE
+ *                         sweep per unordered pair a <= b -- the sweep of (a, b) also contracts its sensitivities with the rows
+ *                         of X_a per node column, which is d k(X_b, X_a) / d X_b, the term of the ordered pair (b, a)
+ *                         (cython_backend.pyx:76-97 solves the triangle only in the forward; here the backward does too):
+ *                         half the sweeps of the GRAM call it replaces, same weights, same out_scale.  Workspace: skb_bwd_vjp_workspace_bytes (smaller is accepted: without room for
  *                         one pair's grid + gradients the stored-grid fallback is not queued; the flag word at byte 64 of
  *                         the workspace is then the caller's to check -- non-zero = a rebuilt grid missed its boundary
  *                         by more than 1e-10 and the result should be recomputed with skb_sigkernel_fwd_bwd).

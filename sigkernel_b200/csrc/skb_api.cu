@@ -703,9 +703,9 @@ int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype, int A, int
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
     if (rc) return rc;
     // pairs = SYM (Gram(X, X), Y = X): ONE reversed sweep per unordered pair a <= b yields both d k / d X_a and d k / d X_b
-    // (MODE_REV_RECON_SYM); loss-head weights only, no per-pair output
+    // (MODE_REV_RECON_SYM), i.e. the terms of the ordered pairs (a, b) and (b, a); no per-pair output
     const bool usym = pairs == SKB_PAIRS_SYM;
-    if (usym && (ctx_pairs != SKB_PAIRS_SYM || A != B || M != N || grad_out || grad_points || !gradX)) return SKB_ERR_BAD_ENUM;
+    if (usym && (ctx_pairs != SKB_PAIRS_SYM || A != B || M != N || grad_points || !gradX)) return SKB_ERR_BAD_ENUM;
     if (ctx_pairs != pairs && !(ctx_pairs == SKB_PAIRS_SYM && pairs == SKB_PAIRS_GRAM && A == B && M == N)) return SKB_ERR_BAD_ENUM;
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
@@ -756,21 +756,19 @@ int skb_sigkernel_bwd_vjp(const void* X, const void* Y, int io_dtype, int A, int
     set_ctx(ra, const_cast<void*>(ctx), njobs_of(A, B, ctx_pairs), M, N, dyadic_order);
     ra.bsym = ctx_pairs == SKB_PAIRS_SYM && pairs != SKB_PAIRS_SYM;
     ra.flag = flag; ra.recon_tol = kReconTol;
-    // unordered pairs: sum over the ORDERED pairs of coef (a, b) d k(X_a, X_b) / d X = for a < b twice the weight on the one
-    // sweep that stands for (a, b) and (b, a); the diagonal pair's sweep already yields both of its terms
-    ra.gout = grad_out; ra.gradX = gradX ? gtmp : nullptr; ra.w_diag = w_diag; ra.w_off = usym ? 2.0 * w_off : w_off;
+    ra.gout = grad_out; ra.gradX = gradX ? gtmp : nullptr; ra.w_diag = w_diag; ra.w_off = w_off;
     rc = launch_recon5(usym ? MODE_REV_RECON_SYM : MODE_REV_RECON, kind5, dyadic_order, ra, st);
     if (rc) return rc;
     if (!fallback) return gradX ? launch_combine(gradX, gtmp, (size_t)A * M * D, out_scale, out_scale_dev, accumulate, st) : SKB_OK;
     // stored-grid fallback behind a device-side test of the flag: forward with store, reversed sweep, loss head
-    // (unordered pairs: the fallback runs over the full square with only d / d first argument -- twice the weights)
+    // (unordered pairs: the fallback runs over the full square, one sweep per ordered pair -- the same sum)
     KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, usym ? SKB_PAIRS_GRAM : pairs);
     fa.Xp = Xp; fa.Yp = Yp; fa.out = (double*)(w + fixed); fa.counter = counter; fa.Dp = Dp; fa.D = D;
     KArgs rb = fa;
     rb.Xp = Xr; rb.Yp = Yr; rb.out = nullptr; rb.grad = grad_points;
     rb.gscale = ra.gscale;
     fa.cond = rb.cond = flag;
-    VjpOpts vo = {grad_out, usym ? 2.0 * w_diag : w_diag, usym ? 2.0 * w_off : w_off, gtmp};
+    VjpOpts vo = {grad_out, w_diag, w_off, gtmp};
     if (gradX) {
         rc = launch_cond_zero(gtmp, (size_t)A * M * D, flag, st);
         if (rc) return rc;

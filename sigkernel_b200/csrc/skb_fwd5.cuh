@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     const int b = p.pairs == PAIRS_BATCH ? a
                                   : (RSYM ? a + (int)(pi - ((long)a * p.A - (long)a * (a - 1) / 2)) : (int)(pi - (long)a * p.B));
                     // fused loss head: d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
-                    const double coef = p.gradX == nullptr ? 0.0 : (p.gout ? __ldg(p.gout + pi) : (a == b ? p.w_diag : p.w_off));
+                    const double coef = p.gradX == nullptr ? 0.0 : (p.gout ? __ldg(p.gout + (RSYM ? (long)a * p.B + b : pi)) : (a == b ? p.w_diag : p.w_off));
                     double* gx = p.gradX ? p.gradX + (long)a * (M * D) : nullptr;
                     double* gpair = p.grad ? p.grad + pi * (long)(M * D) : nullptr;
                     const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + (unsigned)ent.y);
@@ -1144,10 +1144,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         }
                     }
                     if (RSYM) {
-                        // d loss / d X_b += coef * d k(X_a, X_b) / d X_b from the column sums the last lane collected
-                        // (node columns are reversed like the rows: column q is point N - 1 - q of X_b)
+                        // the ordered pair (b, a): d loss / d X_b += coef(b, a) * d k(X_b, X_a) / d X_b, and d k(X_b, X_a) / d X_b
+                        // = d k(X_a, X_b) / d X_b comes from the column sums the last lane collected (node columns are
+                        // reversed like the rows: column q is point N - 1 - q of X_b).  The diagonal pair has no partner.
                         __syncwarp();
-                        if (coef != 0.0) {
+                        const double coef2 = a == b ? 0.0 : (p.gout ? __ldg(p.gout + (long)b * p.B + a) : p.w_off);
+                        if (coef2 != 0.0) {
                             double* gxb = p.gradX + (long)b * (M * D);
                             const double* syb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + (unsigned)ent.z);
                             for (int q = lane; q < N; q += 32) {
@@ -1157,7 +1159,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                 for (int k = 0; k < D; ++k) {
                                     const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(-p.gscale * __ldg(yrw + 1 + k), sW, part[1 + k])
                                                                        : p.inv_kscale * part[1 + k];
-                                    atomicAdd(gxb + (N - 1 - q) * D + k, coef * gv);
+                                    atomicAdd(gxb + (N - 1 - q) * D + k, coef2 * gv);
                                 }
                             }
                         }

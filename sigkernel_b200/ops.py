@@ -230,8 +230,8 @@ def sigkernel_forward_ctx(X, Y, static_kind, static_param, dyadic_order, pairs="
 def sigkernel_backward_vjp(X, Y, static_kind, static_param, dyadic_order, pairs, ctx, ctx_pairs, grad_out=None,
                            w_diag=0.0, w_off=0.0, out_scale=1.0, out_scale_dev=None, into=None, want_points=False,
                            naive=False):
-    """pairs 'sym' (Y is X, ctx_pairs 'sym', w_diag / w_off only): one sweep per unordered pair, gradient w.r.t. both
-    arguments -- gradX = sum over ordered pairs (a,b) of coef(a,b) d k(X_a,X_b)/d X.  Otherwise:
+    """pairs 'sym' (Y is X, ctx_pairs 'sym'): the same sum from one sweep per unordered pair (the sweep of (a,b) also yields
+    the term of (b,a)).  Otherwise:
     Reversed sweep over every ordered pair of `pairs` ('gram' / 'batch') contracted with d loss / d K on the fly:
     gradX (A,M,D) fp64 = [into +] out_scale * [out_scale_dev] * sum_b coef(a,b) d k(X_a,Y_b)/d X_a, coef = grad_out[a,b]
     or (w_diag on a == b, w_off elsewhere).  `ctx` comes from sigkernel_forward_ctx(..., ctx_pairs).  The (A,B,M,D)

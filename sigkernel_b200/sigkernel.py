@@ -141,11 +141,14 @@ class _SigKernelGram(torch.autograd.Function):
                 # with gradients the full square is solved even when symmetric: the reversed sweep runs over every
                 # ordered pair and rebuilds each grid from ITS OWN last row / column (the transposed boundaries of (b, a)
                 # differ from those of (a, b) in the last bits, which the backward recurrence amplifies past the check)
-                res = ops.sigkernel_forward_ctx(X, Y, kind, param, dyadic_order, "gram", _naive_solver)
+                # (unless the unordered-pair sweep covers the shape: it runs the pair (a, b), a <= b, once, from its own
+                #  boundaries, and gets the term of (b, a) out of the same sensitivities)
+                gpairs = "sym" if sym and ops.adjoint_sym_supported(X.shape[1], X.shape[2], dyadic_order, kind, _naive_solver) else "gram"
+                res = ops.sigkernel_forward_ctx(X, Y, kind, param, dyadic_order, gpairs, _naive_solver)
                 if res is not None:
                     G, bctx = res
                     ctx.mode = "lazy"
-                    ctx.meta = (kind, param, dyadic_order, _naive_solver, "gram")
+                    ctx.meta = (kind, param, dyadic_order, _naive_solver, gpairs)
                     ctx.save_for_backward(X, Y, bctx)
                 else:
                     # like the reference, the whole backward is computed eagerly (sigkernel.py:397-399)
@@ -180,7 +183,7 @@ class _SigKernelGram(torch.autograd.Function):
         if ctx.mode == "lazy":
             X, Y, bctx = ctx.saved_tensors
             kind, param, d, naive, pairs = ctx.meta
-            grad = ops.sigkernel_backward_vjp(X, Y, kind, param, d, "gram", bctx, pairs, grad_out=grad_output,
+            grad = ops.sigkernel_backward_vjp(X, Y, kind, param, d, pairs, bctx, pairs, grad_out=grad_output,
                                               out_scale=scale, naive=naive)
         else:
             (gp,) = ctx.saved_tensors
@@ -237,10 +240,8 @@ class _SigLoss(torch.autograd.Function):
             P, Q = T[first], T[second]
             if need_grad and gscale is not None:
                 if pairs == "sym":
-                    if ops.adjoint_sym_supported(P.shape[1], P.shape[2], dyadic_order, kind, _naive_solver):
-                        gscale = 1.0      # one reversed sweep per unordered pair yields both halves of the gradient
-                    else:
-                        pairs = "gram"    # else the full square is solved (see _SigKernelGram.forward)
+                    if not ops.adjoint_sym_supported(P.shape[1], P.shape[2], dyadic_order, kind, _naive_solver):
+                        pairs = "gram"    # no unordered-pair sweep for this shape: the full square is solved
                 G, bctx = ops.sigkernel_forward_ctx(P, Q, kind, param, dyadic_order, pairs, _naive_solver)
                 plan.append((second, pairs, w_diag, w_off, gscale, len(saved)))
                 saved.append(bctx)

@@ -266,16 +266,22 @@ def test_unordered_pair_sweep_matches_the_full_square(skb, O, A, M, D, d, static
     res = skb.ops.sigkernel_forward_ctx(Xc, Xc, static, par, d, "sym")
     assert res is not None
     G, bctx = res
-    g_sym = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", w_diag=w_diag, w_off=w_off)
-    # oracle: sum over ordered pairs of coef(a,b) k(X_a, X_b), gradient w.r.t. both arguments = 2 * sum_b coef d1 k (coef symmetric)
+    g_sym = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", w_diag=w_diag, w_off=w_off, out_scale=2.0)
+    # oracle: out_scale * sum_b coef(a,b) d1 k(X_a, X_b)
     ok = O.RBFKernel(par) if static == "rbf" else O.LinearKernel()
     _, gp_ref, _ = O.gram_grad_points_analytic(X, X, ok, d)
     coef = torch.full((A, A), w_off, dtype=torch.float64) + (w_diag - w_off) * torch.eye(A, dtype=torch.float64)
     expect = 2.0 * torch.einsum('ab,abmd->amd', coef, gp_ref)
     assert grad_err(g_sym.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
     g_diag = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", w_diag=1.0, w_off=0.0)
-    expect = 2.0 * torch.einsum('aamd->amd', gp_ref)
+    expect = torch.einsum('aamd->amd', gp_ref)
     assert grad_err(g_diag.cpu().numpy(), expect.numpy()) <= 1e-6
+    # a general (asymmetric) upstream gradient: g[a] = sum_b w[a,b] d1 k(X_a, X_b), the term of (b,a) from the sweep of (a,b)
+    w = torch.linspace(-1.0, 2.0, A * A, dtype=torch.float64).reshape(A, A)
+    w = w - torch.diag(torch.diag(w))            # (the diagonal pairs are checked above with their own tolerance)
+    g_w = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", grad_out=w.cuda())
+    expect = torch.einsum('ab,abmd->amd', w, gp_ref)
+    assert grad_err(g_w.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
     # and the public loss head with the sweep switched off (mode 3) gives the same gradient
     Y = make_paths("bm", 901 + M, (A + 1, M, D)).cuda()
     sk = skb.SigKernel(skb.RBFKernel(par) if static == "rbf" else skb.LinearKernel(), d)
