@@ -250,6 +250,22 @@ def test_backward_of_any_length_vs_analytic_oracle(skb, O, A, B, M, N, D, d, nai
     assert grad_err(Xg.grad.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
 
 
+def test_batch_backward_of_any_length_vs_analytic_oracle(skb, O):
+    """compute_kernel (pairs = batch) beyond the register-resident adjoint kernels: the materialised-grid path."""
+    X, Y = make_paths("bm", 71, (3, 700, 2)), make_paths("bm", 72, (3, 8, 2))
+    for static, ok, par in (("rbf", O.RBFKernel(1.3), 1.3), ("linear", O.LinearKernel(0.5), 0.25)):
+        assert skb.ops.adjoint_plan(700, 8, 2, 1, static) == 7
+        kref, gp_ref, _ = O.batch_grad_points_analytic(X, Y, ok, 1)
+        k, gp = skb.ops.sigkernel_forward_backward(X.cuda(), Y.cuda(), static, par, 1, "batch")
+        assert gp.shape == (3, 700, 2)
+        assert fwd_err(k.cpu().numpy(), kref.numpy()) <= FWD_TOL
+        assert grad_err(gp.cpu().numpy(), gp_ref.numpy()) <= GRAD_TOL_ANALYTIC
+    Xg = X.cuda().requires_grad_(True)
+    skb.SigKernel(skb.RBFKernel(1.3), 1).compute_kernel(Xg, Y.cuda()).sum().backward()
+    kref, gp_ref, _ = O.batch_grad_points_analytic(X, Y, O.RBFKernel(1.3), 1)
+    assert grad_err(Xg.grad.cpu().numpy(), gp_ref.numpy()) <= GRAD_TOL_ANALYTIC
+
+
 @pytest.mark.parametrize("A,M,D,d,static", [(9, 20, 3, 1, "rbf"), (6, 64, 3, 1, "rbf"), (5, 33, 5, 2, "rbf"), (4, 60, 2, 0, "linear"),
                                             (7, 12, 2, 3, "rbf"), (3, 64, 2, 0, "rbf"), (4, 30, 8, 1, "linear")])
 def test_unordered_pair_sweep_matches_the_full_square(skb, O, A, M, D, d, static):
