@@ -126,6 +126,8 @@ size_t skb_fwd_workspace_bytes(int A, int B, int M, int N, int D, int dyadic_ord
 /* from_static (A,B,M,N as passed there) / solve_increments (A = B = P, M = MM+1, N = NN+1, dyadic_order 0,
  * pairs = SKB_PAIRS_BATCH) */
 size_t skb_aux_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs);
+/* skb_sigkernel_sensitivity_from_static (any length: materialised grids beyond the register-resident kernels) */
+size_t skb_sensitivity_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs);
 /* Recommended size for skb_sigkernel_fwd_bwd / skb_sigkernel_sensitivity_from_static: prepared paths, the boundary
  * context of the adjoint by reconstruction, and room for the forward grids of the stored-grid kernels (all pairs, capped
  * at 8 GiB; 1 GiB when they are only the fallback of the reconstruction).  Any size >= the fixed part + ONE pair's grid

@@ -43,6 +43,7 @@ SYMBOLS = {
     "skb_sigkernel_fwd_range": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _l, _l, _vp, _vp, _i, _vp, _i, ctypes.c_ulonglong, _vp, _sz, _vp]),
     "skb_static_gram": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _d, _i, _vp, _vp, _sz, _vp]),
     "skb_aux_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "skb_sensitivity_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "skb_sigkernel_fwd_from_static": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_sigkernel_solve_increments": (_i, [_vp, _l, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "skb_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),

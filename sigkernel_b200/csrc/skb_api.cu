@@ -326,6 +326,30 @@ static int run_materialized_adjoint(int kind, const KArgs& a, int d, long njobs,
     return SKB_OK;
 }
 
+// plugin kernels: Ks (njobs, M, N) given; out (njobs), S (njobs, M-1, N-1)
+static int run_materialized_sensitivity(const double* Ks, int M, int N, int d, bool s1, double scale4, long njobs, double* out, double* S,
+                                        char* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if ((((long)(M - 1)) << d) > 0x3fffffffL || (((long)(N - 1)) << d) > 0x3fffffffL) return SKB_ERR_BAD_SHAPE;
+    const size_t MMf = (size_t)(M - 1) << d, NNf = (size_t)(N - 1) << d;
+    const size_t per = ((size_t)(M - 1) * (N - 1) + 2 * (MMf + 1) * (NNf + 1)) * sizeof(double);
+    if (scratch_bytes < per + 512) return SKB_ERR_WORKSPACE;
+    long chunk = (long)((scratch_bytes - 512) / per);
+    if (chunk > njobs) chunk = njobs;
+    double* base = (double*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    for (long j0 = 0; j0 < njobs; j0 += chunk) {
+        const long nj = njobs - j0 < chunk ? njobs - j0 : chunk;
+        double* incc = base;
+        double* U = incc + (size_t)nj * (M - 1) * (N - 1);
+        int rc = launch_coarse_increments(Ks + (size_t)j0 * M * N, incc, nj, M, N, scale4, false, st);
+        if (rc) return rc;
+        rc = launch_grid_solve(incc, U, out, j0, nj, M, N, d, s1, st);
+        if (rc) return rc;
+        rc = launch_coarse_sens(U, S + (size_t)j0 * (M - 1) * (N - 1), nj, M, N, d, scale4, st);
+        if (rc) return rc;
+    }
+    return SKB_OK;
+}
+
 // fixed part: counter block, prepared paths in both orientations, [boundary context]; then the stored-grid scratch
 static size_t bwd_workspace_bytes(int A, int B, int M, int N, int D, int d, int pairs, bool with_ctx, bool with_vjp) {
     if (A <= 0 || B <= 0 || M < 2 || N < 2 || D <= 0 || d < 0) return 0;
@@ -797,6 +821,19 @@ int skb_gram_weighted_sum(const double* G, int A, int B, int pairs, double w_dia
     return check_launch();
 }
 
+size_t skb_sensitivity_workspace_bytes(int A, int B, int M, int N, int dyadic_order, int pairs) {
+    if (A <= 0 || B <= 0 || M < 2 || N < 2 || dyadic_order < 0 || dyadic_order > 20) return 0;
+    if (solver_rows_per_lane(M, dyadic_order) >= 0) return bwd_workspace_bytes(A, B, M, N, 1, dyadic_order, pairs, true, false);
+    // materialised grids: coarse increments + the two fine grids of a chunk of pairs
+    const size_t MMf = (size_t)(M - 1) << dyadic_order, NNf = (size_t)(N - 1) << dyadic_order;
+    const size_t per = ((size_t)(M - 1) * (N - 1) + 2 * (MMf + 1) * (NNf + 1)) * sizeof(double);
+    size_t jobs = (size_t)njobs_of(A, B, pairs == SKB_PAIRS_BATCH ? SKB_PAIRS_BATCH : SKB_PAIRS_GRAM);
+    size_t cap = kMaterializedBudget / per;
+    if (cap < 1) cap = 1;
+    if (jobs > cap) jobs = cap;
+    return kCounterBytes + jobs * per + 1024;
+}
+
 int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M, int N, int dyadic_order,
                                           int scheme, int pairs, double* out, double* S, void* workspace,
                                           size_t workspace_bytes, void* stream) {
@@ -807,6 +844,9 @@ int skb_sigkernel_sensitivity_from_static(const double* Ks, int A, int B, int M,
     if (!workspace || workspace_bytes < kCounterBytes) return SKB_ERR_WORKSPACE;
     const long nj = njobs_of(A, B, pairs);
     if (nj > 0x7fffffffL) return SKB_ERR_BAD_SHAPE;
+    if (solver_rows_per_lane(M, dyadic_order) < 0)       // beyond the register-resident kernels: materialised grids, any length
+        return run_materialized_sensitivity(Ks, M, N, dyadic_order, scheme == SKB_SCHEME_S1, scale4_of(dyadic_order), nj, out, S,
+                                            (char*)workspace + kCounterBytes, workspace_bytes - kCounterBytes, (cudaStream_t)stream);
     KArgs fa = base_args(A, B, M, N, dyadic_order, scheme, pairs);
     fa.Ks = Ks; fa.out = out; fa.counter = (unsigned int*)workspace;
     KArgs ra = fa;

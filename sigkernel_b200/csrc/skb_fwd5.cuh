@@ -216,7 +216,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
     }
     const int glane = threadIdx.x;               // position in the wavefront
     const int lane = glane & 31;
-    const int wid = glane >> 5;
     const int pl = LPP == 32 ? glane : (lane & (LPP - 1));   // position in the pair's wavefront
     const int sid = LPP == 32 ? 0 : lane / LPP;               // pair stream of this lane
     const int slot = LPP == 32 ? glane : sid * (LPP + 1) + pl;   // exchange slot (one boundary slot per stream)

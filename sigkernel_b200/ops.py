@@ -294,7 +294,7 @@ def sensitivity_from_static(Ks, dyadic_order, pairs="gram", naive=False):
         n = _n_out(A, B, pairs)
         out = torch.empty(n, dtype=torch.float64, device=Kc.device)
         S = torch.empty((n, M - 1, N - 1), dtype=torch.float64, device=Kc.device)
-        ws, nbytes = _workspace(lib.skb_bwd_workspace_bytes(A, B, M, N, 1, int(dyadic_order), _PAIRS[pairs]), Kc.device)
+        ws, nbytes = _workspace(lib.skb_sensitivity_workspace_bytes(A, B, M, N, int(dyadic_order), _PAIRS[pairs]), Kc.device)
         check(lib.skb_sigkernel_sensitivity_from_static(Kc.data_ptr(), A, B, M, N, int(dyadic_order),
                                                         _lib.SCHEME_S1 if naive else _lib.SCHEME_S2,
                                                         _PAIRS[pairs], out.data_ptr(), S.data_ptr(),

@@ -108,6 +108,18 @@ def test_sensitivity_from_static_vs_oracle(skb, O, d):
     assert grad_err(S.cpu().numpy(), Sref.numpy()) <= 1e-11
 
 
+def test_sensitivity_from_static_of_a_long_path_vs_oracle(skb, O):
+    """Plugin path beyond the register-resident kernels (materialised grids): forward value and coarse sensitivities."""
+    X, Y = make_paths("bm", 53, (2, 400, 2)), make_paths("bm", 54, (2, 9, 2))
+    sk = O.RBFKernel(0.9)
+    for d, naive in ((1, False), (2, True)):
+        Gref, _, Sref = O.gram_grad_points_analytic(X, Y, sk, d, naive=naive)
+        G, S = skb.ops.sensitivity_from_static(sk.Gram_matrix(X, Y).cuda(), d, "gram", naive)
+        assert S.shape == (2, 2, 399, 8)
+        assert fwd_err(G.cpu().numpy(), Gref.numpy()) <= FWD_TOL
+        assert grad_err(S.cpu().numpy(), Sref.numpy()) <= 1e-11
+
+
 def test_plugin_kernel_gradient_matches_reference_formula(skb, O):
     """User-defined static kernel: finite-difference route (as the reference) on top of the CUDA S."""
     class Poly:
