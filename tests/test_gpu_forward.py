@@ -371,3 +371,40 @@ def test_overflowing_pair_does_not_leak_into_its_stream(skb, O):
             skb._lib.lib.skb_set_warps_per_sm(0)
         assert (~np.isfinite(got[2])).all()
         assert fwd_err(got[~bad], ref[~bad]) <= FWD_TOL
+
+
+@pytest.mark.parametrize("pairs", ["gram", "sym"])
+def test_forward_range_slices_assemble_the_full_matrix(skb, pairs):
+    """skb_sigkernel_fwd_range: slices of the pair enumeration (one rank's share of a sharded Gram matrix) written into a
+    local matrix, and -- with one "peer", this device -- through the peer-store path with the in-kernel rank barrier."""
+    X = make_paths("rand", 7, (11, 20, 3)).cuda()
+    Y = X if pairs == "sym" else make_paths("rand", 8, (9, 17, 3)).cuda()
+    sk = skb.SigKernel(skb.RBFKernel(0.5), 1)
+    ref = sk.compute_Gram(X, Y, sym=pairs == "sym")
+    A, B = X.shape[0], Y.shape[0]
+    total = skb.ops.n_jobs(A, B, pairs)
+    out = torch.full((A, B), float("nan"), dtype=torch.float64, device="cuda")
+    cuts = [0, total // 3, total // 3, (2 * total) // 3 + 1, total]          # includes an empty slice
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        assert skb.ops.sigkernel_forward_range(X, Y, "rbf", 0.5, 1, lo, hi, pairs, out=out)
+    assert torch.equal(out, ref)
+    # peer stores into "every rank's copy" (here: one) + the kernel's own barrier: slot 0 of the signal array reaches the epoch
+    buf = torch.full((A, B), float("nan"), dtype=torch.float64, device="cuda")
+    sig = torch.zeros(8, dtype=torch.int64, device="cuda")
+    for epoch, (lo, hi) in enumerate(((0, total // 2), (total // 2, total), (total, total)), start=1):
+        assert skb.ops.sigkernel_forward_range(X, Y, "rbf", 0.5, 1, lo, hi, pairs, peer_ptrs=[buf.data_ptr()],
+                                               signal=([sig.data_ptr()], 0, epoch))
+        torch.cuda.synchronize()
+        assert int(sig[0]) == epoch
+    assert torch.equal(buf, ref)
+
+
+def test_static_gram_matches_the_plugin_kernels(skb):
+    """skb_static_gram (one CUDA pass) against the torch implementation behind the plugin interface."""
+    X, Y = make_paths("rand", 3, (4, 9, 3)).cuda(), make_paths("rand", 4, (5, 7, 3)).cuda()
+    for k, kind, par in ((skb.RBFKernel(0.7), "rbf", 0.7), (skb.LinearKernel(), "linear", 1.0)):
+        K = skb.ops.static_gram(X, Y, kind, par, "gram")
+        assert K.shape == (4, 5, 9, 7)
+        assert fwd_err(K.cpu().numpy(), k.Gram_matrix(X, Y).cpu().numpy()) <= 1e-14
+    Kb = skb.ops.static_gram(X, Y[:4, :, :], "rbf", 0.7, "batch")
+    assert fwd_err(Kb.cpu().numpy(), skb.RBFKernel(0.7).batch_kernel(X, Y[:4]).cpu().numpy()) <= 1e-14
