@@ -233,7 +233,11 @@ int skb_sigkernel_solve_increments(const double* inc, long P, int MM, int NN, in
  *                              with the ANALYTIC static-kernel derivative in place of the reference's
  *                              h = 1e-9 one-sided finite difference (agrees with it to its own noise floor,
  *                              SURVEY.md 8(a)).
- * `pairs` is SKB_PAIRS_GRAM or SKB_PAIRS_BATCH (a symmetric Gram needs every (a,b) gradient anyway).
+ * `pairs` is SKB_PAIRS_GRAM, SKB_PAIRS_BATCH or SKB_PAIRS_SYM (Y = X: out (A, A) and grad_points (A, A, M, D) are the FULL
+ * tensors -- a symmetric Gram needs every (a, b) gradient -- but where the unordered-pair sweep covers the shape
+ * (skb_adjoint_sym_supported) they come from one forward solve and one reversed sweep per pair a <= b: the sweep of (a, b)
+ * yields d k(X_a,X_b) / d X_a and, from the same sensitivities, d k(X_b,X_a) / d X_b; cython_backend.pyx:76-97 exploits the
+ * symmetry in the forward only).
  */
 int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype,
                           int A, int B, int M, int N, int D, int dyadic_order,

@@ -606,12 +606,18 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
                           void* stream) {
     int rc = check_common(A, B, M, N, dyadic_order, scheme, pairs, SKB_ARITH_FMA);
     if (rc) return rc;
-    if (pairs == SKB_PAIRS_SYM) return SKB_ERR_BAD_ENUM;
     if (D <= 0) return SKB_ERR_BAD_SHAPE;
     if (static_kind != SKB_STATIC_LINEAR && static_kind != SKB_STATIC_RBF) return SKB_ERR_BAD_ENUM;
     if (io_dtype != SKB_F64 && io_dtype != SKB_F32) return SKB_ERR_BAD_ENUM;
     if (!X || !Y || !out || !grad_points) return SKB_ERR_NULL;
     if (!workspace) return SKB_ERR_WORKSPACE;
+    // SYM (Y = X): out and grad_points are the full (A, A) / (A, A, M, D) tensors; one forward solve and one reversed sweep per
+    // unordered pair where the unordered-pair sweep covers the shape, the full square otherwise (the same numbers)
+    const bool sym_sweep = pairs == SKB_PAIRS_SYM && recon_ok(static_kind, A, B, M, N, D, dyadic_order, scheme) &&
+                           recon5_sym_applies(static_kind == SKB_STATIC_RBF ? KIND_RBF : KIND_LINEAR, M, N, D, dyadic_order, scheme == SKB_SCHEME_S1);
+    if (pairs == SKB_PAIRS_SYM && !sym_sweep)
+        return skb_sigkernel_fwd_bwd(X, Y, io_dtype, A, B, M, N, D, dyadic_order, static_kind, static_param, scheme, SKB_PAIRS_GRAM, out,
+                                     grad_points, workspace, workspace_bytes, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int Dp = padded_dim(D);
     const size_t xb = align256((size_t)A * M * Dp * sizeof(double)), yb = align256((size_t)B * N * Dp * sizeof(double));
@@ -676,10 +682,16 @@ int skb_sigkernel_fwd_bwd(const void* X, const void* Y, int io_dtype, int A, int
         rc = launch_recon5(MODE_FWD_EMIT, kind5, dyadic_order, fa, st);
         if (rc) return rc;
         ra.flag = flag; ra.recon_tol = kReconTol;
-        rc = launch_recon5(MODE_REV_RECON, kind5, dyadic_order, ra, st);
+        rc = launch_recon5(sym_sweep ? MODE_REV_RECON_SYM : MODE_REV_RECON, kind5, dyadic_order, ra, st);
         if (rc) return rc;
         if (!fallback) return SKB_OK;
         fa.cond = ra.cond = flag;            // queued behind a device-side test of the flag
+        if (sym_sweep) {
+            // the stored-grid kernels run over the ordered pairs of the full square (same out, same grad_points)
+            fa.pairs = ra.pairs = SKB_PAIRS_GRAM;
+            return run_adjoint(kind5, MODE_REV_GRAD, fa, ra, dyadic_order, njobs_of(A, B, SKB_PAIRS_GRAM), (double*)(w + fixed),
+                               workspace_bytes - fixed, st, v5);
+        }
     }
     return run_adjoint(kind5, MODE_REV_GRAD, fa, ra, dyadic_order, nj, (double*)(w + fixed), workspace_bytes - fixed, st, v5);
 }

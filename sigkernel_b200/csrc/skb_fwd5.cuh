@@ -1093,7 +1093,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                     // fused loss head: d loss / d X_a += coef * d k(X_a, Y_b) / d X_a
                     const double coef = p.gradX == nullptr ? 0.0 : (p.gout ? __ldg(p.gout + (RSYM ? (long)a * p.B + b : pi)) : (a == b ? p.w_diag : p.w_off));
                     double* gx = p.gradX ? p.gradX + (long)a * (M * D) : nullptr;
-                    double* gpair = p.grad ? p.grad + pi * (long)(M * D) : nullptr;
+                    // per-pair gradient rows (A, B, M, D): the unordered-pair sweep fills (a, b) here and (b, a) from its column sums
+                    double* gpair = p.grad ? p.grad + (RSYM ? (long)a * p.B + b : pi) * (long)(M * D) : nullptr;
                     const double* sxb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Xp) + (unsigned)ent.y);
                     const double* fs = gst + (size_t)(fw & p.fbuf_mask) * FBUF + glane;
                     const double2* fs2 = reinterpret_cast<const double2*>(gst + (size_t)(fw & p.fbuf_mask) * FBUF) + glane;
@@ -1147,8 +1148,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                         // = d k(X_a, X_b) / d X_b comes from the column sums the last lane collected (node columns are
                         // reversed like the rows: column q is point N - 1 - q of X_b).  The diagonal pair has no partner.
                         __syncwarp();
-                        const double coef2 = a == b ? 0.0 : (p.gout ? __ldg(p.gout + (long)b * p.B + a) : p.w_off);
-                        if (coef2 != 0.0) {
+                        const double coef2 = (a == b || p.gradX == nullptr) ? 0.0 : (p.gout ? __ldg(p.gout + (long)b * p.B + a) : p.w_off);
+                        double* gpair2 = (p.grad && a != b) ? p.grad + ((long)b * p.B + a) * (long)(M * D) : nullptr;
+                        if (coef2 != 0.0 || gpair2 != nullptr) {
                             double* gxb = p.gradX + (long)b * (M * D);
                             const double* syb = reinterpret_cast<const double*>(reinterpret_cast<const char*>(p.Yp) + (unsigned)ent.z);
                             for (int q = lane; q < N; q += 32) {
@@ -1158,7 +1160,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) fwd5_kernel(const KArgs p) {
                                 for (int k = 0; k < D; ++k) {
                                     const double gv = KIND == KIND_RBF ? p.inv_kscale * fma(-p.gscale * __ldg(yrw + 1 + k), sW, part[1 + k])
                                                                        : p.inv_kscale * part[1 + k];
-                                    atomicAdd(gxb + (N - 1 - q) * D + k, coef2 * gv);
+                                    if (gpair2) gpair2[(N - 1 - q) * D + k] = gv;
+                                    if (coef2 != 0.0) atomicAdd(gxb + (N - 1 - q) * D + k, coef2 * gv);
                                 }
                             }
                         }

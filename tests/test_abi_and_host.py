@@ -52,7 +52,8 @@ def test_argument_validation_codes_without_gpu():
     assert f(None, None, 0, 2, 2, 4, 4, 2, 0, 1, 1.0, 0, 0, 0, None, None, 0, None) == -6      # NULL pointers
     assert f(1, 1, 0, 2, 2, 4, 4, 2, 0, 1, 1.0, 0, 0, 0, 1, None, 0, None) == -3               # workspace
     assert lib.skb_sigkernel_solve_increments(None, 0, 4, 4, 0, 0, None, None, 0, None) == -1
-    assert lib.skb_sigkernel_fwd_bwd(None, None, 0, 2, 2, 4, 4, 2, 0, 1, 1.0, 0, 2, None, None, None, 0, None) == -2
+    assert lib.skb_sigkernel_fwd_bwd(None, None, 0, 2, 2, 4, 4, 2, 0, 1, 1.0, 0, 2, None, None, None, 0, None) == -6      # SYM is accepted
+    assert lib.skb_sigkernel_fwd_bwd(None, None, 0, 2, 3, 4, 4, 2, 0, 1, 1.0, 0, 2, None, None, None, 0, None) == -1      # ... for A == B
     assert lib.skb_fp64_probe(0, 1, 512, 1, None, None) == -1
 
 

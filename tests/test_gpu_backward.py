@@ -310,6 +310,13 @@ def test_unordered_pair_sweep_matches_the_full_square(skb, O, A, M, D, d, static
     g_w = skb.ops.sigkernel_backward_vjp(Xc, Xc, static, par, d, "sym", bctx, "sym", grad_out=w.cuda())
     expect = torch.einsum('ab,abmd->amd', w, gp_ref)
     assert grad_err(g_w.cpu().numpy(), expect.numpy()) <= GRAD_TOL_ANALYTIC
+    # the eager entry point with pairs = sym: the full (A, A) / (A, A, M, D) tensors from the triangle of sweeps
+    G2, gp2 = skb.ops.sigkernel_forward_backward(Xc, Xc, static, par, d, "sym")
+    Gg, gpg = skb.ops.sigkernel_forward_backward(Xc, Xc, static, par, d, "gram")
+    assert fwd_err(G2.cpu().numpy(), Gg.cpu().numpy()) <= 1e-13
+    off = ~torch.eye(A, dtype=torch.bool)
+    assert grad_err(gp2.cpu()[off].numpy(), gp_ref[off].numpy()) <= GRAD_TOL_ANALYTIC
+    assert grad_err(gp2.cpu().numpy(), gpg.cpu().numpy()) <= 1e-6           # (diagonal pairs: see above)
     # and the public loss head with the sweep switched off (mode 3) gives the same gradient
     Y = make_paths("bm", 901 + M, (A + 1, M, D)).cuda()
     sk = skb.SigKernel(skb.RBFKernel(par) if static == "rbf" else skb.LinearKernel(), d)
