@@ -1,6 +1,9 @@
 // skb_fwd5.cuh -- the v5 kernel of the fused static kinds (Linear / RBF): the hot path of compute_Gram /
-// compute_kernel (MODE 0, every BASELINE config) and of the adjoint pass behind compute_mmd(...).backward()
-// (MODE_FWD_STORE / MODE_REV_GRAD).  DESIGN.md 3a / 4a have the measurements behind every choice below.
+// compute_kernel (MODE 0, every BASELINE config; S1 = _naive_solver as a template flag) and of the adjoint pass behind
+// compute_mmd(...).backward(): MODE_FWD_EMIT (forward + last row / column of every grid), MODE_REV_RECON (reversed sweep
+// that rebuilds the forward grid backwards) and MODE_REV_RECON_SYM (the same over unordered pairs of Gram(X, X), gradient
+// w.r.t. both paths); MODE_FWD_STORE / MODE_REV_GRAD (stored grid) remain as their device-side fallback.
+// DESIGN.md 3a / 4a have the measurements behind every choice below.
 //
 // Same decomposition as solver_kernel (skb_solver.cuh): a warp streams through path pairs, lane t owns RC coarse
 // rows (R = RC * 2^d fine rows in registers) and runs one macro step (= one coarse column) behind lane t-1.
@@ -21,8 +24,13 @@
 //   * production runs 4 columns ahead of the stencil so that the exchanged d value is one step old;
 //   * the three per-pair events (output, boundary re-arm, production wrap) hang off one test per step;
 //   * the exp() underflow guard is one unsigned min on the high word; constants are constant-bank operands;
-//   * adjoint modes: lane-major stored grid, 256-bit sector stores / loads, the reversed sweep reads its rows
-//     through a per-lane cp.async ring 4 steps ahead, gradient accumulators in registers.
+//   * stored-grid adjoint modes: lane-major grid, 256-bit sector stores / loads, the reversed sweep reads its rows
+//     through a per-lane cp.async ring 4 steps ahead, gradient accumulators in registers;
+//   * reconstruction modes: a second stencil runs the forward recurrence backwards from the emitted boundaries (checked
+//     against u[., 0] = 1 per pair); lanes PARK their per-pair sums in shared memory and the warp emits a pair's gradient
+//     rows once its last lane is through (the skew makes every per-lane event cost the warp a full pass);
+//   * sharded forward: results can go to every rank's copy of G (peer memory), optionally followed by an in-kernel barrier
+//     across the ranks (last block signals and waits).
 //
 // fp64 throughout, FMA arithmetic (u11 = a (u10 + u01) + (-b) u00), results within 1e-13 of solver_kernel.
 // Reference semantics replaced: sigkernel/cuda_backend.py:121-160 (+ :6-49), static_kernels.py:17-33, 42-73,

@@ -140,7 +140,7 @@ int launch_group_adj5_lin_rev(int rc, int logd, int dp2, const KArgs&, cudaStrea
 
 // ---- adjoint by reconstruction (MODE_FWD_EMIT / MODE_REV_RECON of skb_fwd5.cuh) ---------------------------------
 // development / tuning knob (process-wide): -1 / 1 = default (reconstruction, 32 lanes per pair), 0 = stored-grid
-// kernels only, 2 = reconstruction with 16 lanes per pair where instantiated
+// kernels only, 2 = reconstruction with 16 lanes per pair where instantiated, 3 = default without the unordered-pair sweep
 void set_adjoint_mode(int mode);
 int get_adjoint_mode();
 // true if the reconstruction kernels cover the problem (fused kind, scheme S2, len_y >= 4, strips of <= 8 fine rows on
